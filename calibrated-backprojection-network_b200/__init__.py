@@ -1,0 +1,20 @@
+"""kbnet_b200 -- B200-native (sm_100a) implementation of KBNet's SparseToDensePool and Calibrated Backprojection
+layers behind the reference's own nn.Module interface, plus the encoder/decoder wiring around them.
+
+Importable as ``kbnet_b200`` (see kbnet_b200.py at the repository root; this directory keeps the name the build
+contract asks for).  The compute lives in libkbnet_b200.so (csrc/, C ABI in include/kbnet_b200.h).
+"""
+from . import _lib, build as _build, dist, ops
+from .modules import CalibratedBackprojectionBlock, SparseToDensePool, install
+from .model import KBNetEncoder, KBNetModel, MultiScaleDecoder
+
+__all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
+           'install', 'ops', 'dist', 'build_library', 'library_path']
+
+
+def build_library(force=False, verbose=False):
+    return _build.build(force=force, verbose=verbose)
+
+
+def library_path():
+    return _lib.LIB_PATH

@@ -1,0 +1,54 @@
+"""ctypes binding of libkbnet_b200.so (C ABI declared in include/kbnet_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, the caller gets an exception.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
+
+EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_s2d_forward', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
+           'kbnet_conv2d_forward', 'kbnet_depth_head_forward')
+
+
+class KBNetConvSrc(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('C', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
+                ('stride_n', ctypes.c_longlong), ('mode', ctypes.c_int)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('kbnet_b200: %s not found -- build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(there is no CPU / PyTorch fallback for this path)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i, f, ll, sz = c.c_void_p, c.c_int, c.c_float, c.c_longlong, c.c_size_t
+    lib.kbnet_version.restype = i
+    lib.kbnet_last_error.restype = c.c_char_p
+    lib.kbnet_launch_count.restype = c.c_ulonglong
+    lib.kbnet_s2d_forward.restype = i
+    lib.kbnet_s2d_forward.argtypes = [vp, i, i, i, i, c.POINTER(i), i, c.POINTER(i), i, c.POINTER(vp), i, i, vp, f, vp, vp, vp]
+    lib.kbnet_kb_workspace_bytes.restype = sz
+    lib.kbnet_kb_workspace_bytes.argtypes = [i] * 9
+    lib.kbnet_kb_forward.restype = i
+    lib.kbnet_kb_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp, i, f,
+                                     vp, ll, vp, ll, vp, ll, vp, sz, vp]
+    lib.kbnet_conv2d_forward.restype = i
+    lib.kbnet_conv2d_forward.argtypes = [c.POINTER(KBNetConvSrc), i, i, i, i, vp, i, i, i, i, f, vp, ll, vp]
+    lib.kbnet_depth_head_forward.restype = i
+    lib.kbnet_depth_head_forward.argtypes = [vp, ll, c.c_double, c.c_double, vp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().kbnet_last_error()
+        raise RuntimeError('kbnet_b200 %s failed (code %d): %s' % (what, rc, msg.decode() if msg else ''))

@@ -1,0 +1,155 @@
+// extern "C" entry points of libkbnet_b200.so (see include/kbnet_b200.h for the contract).
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace kbnet {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // statistics only (atomic increments)
+
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static ConvSrcDev make_src(const float* ptr, const float* aux, int C, int H, int W, long long stride_n, int mode) {
+    ConvSrcDev s;
+    memset(&s, 0, sizeof(s));
+    s.ptr = ptr; s.aux = aux; s.C = C; s.H = H; s.W = W; s.stride_n = stride_n; s.mode = mode;
+    s.scale_y = s.scale_x = 1.f;
+    return s;
+}
+
+static int finish_conv(ConvParams& p, int N, int Hin, int Win, const float* w, int F, int ksize, int stride, int act,
+                       float slope, float* out, long long out_stride_n) {
+    p.N = N; p.Hin = Hin; p.Win = Win;
+    p.Ctot = 0;
+    for (int i = 0; i < p.n_src; ++i) p.Ctot += p.src[i].C;
+    p.ksize = ksize; p.stride = stride; p.F = F; p.w = w; p.out = out;
+    const int pad = ksize / 2;
+    p.Hout = (Hin + 2 * pad - ksize) / stride + 1;
+    p.Wout = (Win + 2 * pad - ksize) / stride + 1;
+    p.out_stride_n = out_stride_n;
+    p.act = act; p.slope = slope;
+    KB_CHECK_ARG(out_stride_n >= (long long)F * p.Hout * p.Wout, "conv: out_stride_n=%lld smaller than F*Ho*Wo", out_stride_n);
+    return 0;
+}
+
+}  // namespace kbnet
+
+using namespace kbnet;
+
+extern "C" {
+
+int kbnet_version(void) { return KBNET_B200_VERSION; }
+
+const char* kbnet_last_error(void) { return g_err; }
+
+unsigned long long kbnet_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
+                      int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
+                      float* out, float* pyramid, void* stream) {
+    return s2d_forward(x, N, C_in, H, W, min_sizes, n_min, max_sizes, n_max, w_1x1, n_conv, n_filter, w_3x3, neg_slope, out,
+                       pyramid, (cudaStream_t)stream);
+}
+
+size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f) {
+    (void)C_i; (void)C_d; (void)C_f; (void)F_i; (void)F_d; (void)F_f;
+    const size_t Ho = (size_t)(H - 1) / 2 + 1, Wo = (size_t)(W - 1) / 2 + 1;
+    return (((size_t)N * Ho * Wo * sizeof(float)) + 255) & ~(size_t)255;  // z at even pixels
+}
+
+int kbnet_kb_forward(const float* image, long long image_stride_n, const float* depth, long long depth_stride_n,
+                     const float* fused, long long fused_stride_n, const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_image, int F_i, const float* w_depth,
+                     int F_d, const float* w_proj, const float* w_fused, int F_f, float neg_slope, float* out_image,
+                     long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
+                     long long out_fused_stride_n, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    KB_CHECK_ARG(image && depth && w_image && w_depth && w_proj && w_fused && out_image && out_depth && out_fused,
+                 "kb: null pointer argument");
+    KB_CHECK_ARG((coordinates != nullptr) != (kinv != nullptr), "kb: pass exactly one of `coordinates` and `kinv`");
+    KB_CHECK_ARG((fused != nullptr) == (C_f > 0), "kb: fused pointer and C_f=%d disagree", C_f);
+    KB_CHECK_ARG(N >= 0 && C_i > 0 && C_d > 0 && H > 0 && W > 0 && F_i > 0 && F_d > 0 && F_f > 0, "kb: bad shape");
+    if (N == 0) return 0;
+    const long long plane = (long long)H * W;
+    KB_CHECK_ARG(image_stride_n >= C_i * plane && depth_stride_n >= C_d * plane && (!fused || fused_stride_n >= C_f * plane),
+                 "kb: input stride_n smaller than C*H*W");
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const size_t need = kbnet_kb_workspace_bytes(N, C_i, C_d, C_f, H, W, F_i, F_d, F_f);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("kb: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        return KBNET_E_WORKSPACE;
+    }
+    float* z = (float*)workspace;
+    int rc;
+    // conv_image = leaky(conv3x3 s2 (image))                                     net_utils.py:1348
+    {
+        ConvParams p; memset(&p, 0, sizeof(p));
+        p.n_src = 1;
+        p.src[0] = make_src(image, nullptr, C_i, H, W, image_stride_n, SRC_DIRECT);
+        if ((rc = finish_conv(p, N, H, W, w_image, F_i, 3, 2, 1, neg_slope, out_image, out_image_stride_n))) return rc;
+        if ((rc = conv_direct_launch(p, stream))) return rc;
+    }
+    // conv_depth = leaky(conv3x3 s2 (cat[depth, coords]))                        net_utils.py:1351
+    {
+        ConvParams p; memset(&p, 0, sizeof(p));
+        p.n_src = 2;
+        p.src[0] = make_src(depth, nullptr, C_d, H, W, depth_stride_n, SRC_DIRECT);
+        p.src[1] = coordinates ? make_src(coordinates, nullptr, 3, H, W, 3 * plane, SRC_DIRECT)
+                               : make_src(kinv, nullptr, 3, H, W, 9, SRC_COORDS_KINV);
+        if ((rc = finish_conv(p, N, H, W, w_depth, F_d, 3, 2, 1, neg_slope, out_depth, out_depth_stride_n))) return rc;
+        if ((rc = conv_direct_launch(p, stream))) return rc;
+    }
+    // z = leaky(proj_depth(depth)) at even pixels                                net_utils.py:1357
+    if ((rc = kb_proj_z_launch(depth, depth_stride_n, w_proj, N, C_d, H, W, Ho, Wo, neg_slope, z, stream))) return rc;
+    // conv_fused = leaky(conv1x1 s2 (cat[image, coords * z, fused?]))            net_utils.py:1360-1369
+    {
+        ConvParams p; memset(&p, 0, sizeof(p));
+        p.n_src = fused ? 3 : 2;
+        p.src[0] = make_src(image, nullptr, C_i, H, W, image_stride_n, SRC_DIRECT);
+        p.src[1] = coordinates ? make_src(coordinates, z, 3, H, W, 3 * plane, SRC_XYZ_TENSOR)
+                               : make_src(kinv, z, 3, H, W, 9, SRC_XYZ_KINV);
+        p.src[1].zW = Wo; p.src[1].zplane = (long long)Ho * Wo;
+        if (fused) p.src[2] = make_src(fused, nullptr, C_f, H, W, fused_stride_n, SRC_DIRECT);
+        if ((rc = finish_conv(p, N, H, W, w_fused, F_f, 1, 2, 1, neg_slope, out_fused, out_fused_stride_n))) return rc;
+        if ((rc = conv_direct_launch(p, stream))) return rc;
+    }
+    return 0;
+}
+
+int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in, const float* w, int F, int ksize,
+                         int stride, int act, float neg_slope, float* out, long long out_stride_n, void* stream) {
+    KB_CHECK_ARG(srcs && w && out, "conv: null pointer argument");
+    KB_CHECK_ARG(n_src >= 1 && n_src <= CONV_MAX_SRC, "conv: n_src=%d unsupported (1..%d)", n_src, CONV_MAX_SRC);
+    KB_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "conv: ksize=%d stride=%d unsupported", ksize, stride);
+    KB_CHECK_ARG(N >= 0 && H_in > 0 && W_in > 0 && F > 0, "conv: bad shape");
+    if (N == 0) return 0;
+    ConvParams p; memset(&p, 0, sizeof(p));
+    p.n_src = n_src;
+    for (int i = 0; i < n_src; ++i) {
+        const kbnet_conv_src& s = srcs[i];
+        KB_CHECK_ARG(s.ptr && s.C > 0 && s.H > 0 && s.W > 0, "conv: source %d invalid", i);
+        KB_CHECK_ARG(s.mode == 0 || s.mode == 1, "conv: source %d mode %d unsupported", i, s.mode);
+        KB_CHECK_ARG(s.mode == 1 || (s.H == H_in && s.W == W_in), "conv: source %d is %dx%d but the conv input is %dx%d", i,
+                     s.H, s.W, H_in, W_in);
+        p.src[i] = make_src(s.ptr, nullptr, s.C, s.H, s.W, s.stride_n, s.mode ? SRC_UPSAMPLE : SRC_DIRECT);
+        p.src[i].scale_y = (float)s.H / (float)H_in;
+        p.src[i].scale_x = (float)s.W / (float)W_in;
+    }
+    int rc;
+    if ((rc = finish_conv(p, N, H_in, W_in, w, F, ksize, stride, act, neg_slope, out, out_stride_n))) return rc;
+    return conv_direct_launch(p, (cudaStream_t)stream);
+}
+
+int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream) {
+    KB_CHECK_ARG(x && y && n_elem >= 0, "depth_head: bad argument");
+    return depth_head_launch(x, n_elem, min_depth, max_depth, y, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Shared description of a fused convolution: out = act(conv(cat_c(sources), w)).
+#pragma once
+#include "common.cuh"
+
+namespace kbnet {
+
+enum ConvSrcMode {
+    SRC_DIRECT = 0,       // NCHW tensor at the conv input resolution
+    SRC_UPSAMPLE = 1,     // NCHW tensor, nearest-upsampled to the conv input resolution on the fly
+    SRC_COORDS_KINV = 2,  // 3 channels generated from K^-1 (ptr = [N,9]): c(v,u) = k[3c]*u + k[3c+1]*v + k[3c+2]
+    SRC_XYZ_KINV = 3,     // 3 channels coords(K^-1) * z, z = aux [N,1,ceil(H/2),ceil(W/2)] sampled at (iy/2, ix/2)
+    SRC_XYZ_TENSOR = 4,   // 3 channels coordinates tensor (ptr [N,3,H,W]) * z (aux), same sampling
+};
+
+struct ConvSrcDev {
+    const float* ptr;
+    const float* aux;
+    int C, H, W;         // channels and SOURCE spatial size
+    long long stride_n;  // elements between samples of ptr
+    int mode;
+    float scale_y, scale_x;  // SRC_UPSAMPLE: (float)H_src / H_in, (float)W_src / W_in  (torch 'nearest')
+    int zW;                  // SRC_XYZ_*: row pitch of aux;  zplane = elements per sample of aux
+    long long zplane;
+};
+
+constexpr int CONV_MAX_SRC = 4;
+
+struct ConvParams {
+    ConvSrcDev src[CONV_MAX_SRC];
+    int n_src;
+    int N, Hin, Win, Ctot;
+    int ksize, stride;
+    int F;
+    const float* w;  // [F, Ctot, k, k]
+    float* out;      // [N, *, Hout, Wout], sample pitch out_stride_n
+    long long out_stride_n;
+    int Hout, Wout;
+    int act;
+    float slope;
+};
+
+__device__ __forceinline__ float conv_fetch(const ConvSrcDev& S, int n, int c, int iy, int ix) {
+    switch (S.mode) {
+        case SRC_DIRECT:
+            return __ldg(S.ptr + (size_t)n * S.stride_n + ((size_t)c * S.H + iy) * S.W + ix);
+        case SRC_UPSAMPLE: {
+            const int sy = nearest_src(iy, S.scale_y, S.H), sx = nearest_src(ix, S.scale_x, S.W);
+            return __ldg(S.ptr + (size_t)n * S.stride_n + ((size_t)c * S.H + sy) * S.W + sx);
+        }
+        case SRC_COORDS_KINV: {
+            const float* k = S.ptr + (size_t)n * 9 + 3 * c;
+            return fmaf(__ldg(k), (float)ix, fmaf(__ldg(k + 1), (float)iy, __ldg(k + 2)));
+        }
+        case SRC_XYZ_KINV: {
+            const float* k = S.ptr + (size_t)n * 9 + 3 * c;
+            const float co = fmaf(__ldg(k), (float)ix, fmaf(__ldg(k + 1), (float)iy, __ldg(k + 2)));
+            return co * __ldg(S.aux + (size_t)n * S.zplane + (size_t)(iy >> 1) * S.zW + (ix >> 1));
+        }
+        default: {  // SRC_XYZ_TENSOR
+            const float co = __ldg(S.ptr + (size_t)n * S.stride_n + ((size_t)c * S.H + iy) * S.W + ix);
+            return co * __ldg(S.aux + (size_t)n * S.zplane + (size_t)(iy >> 1) * S.zW + (ix >> 1));
+        }
+    }
+}
+
+int conv_direct_launch(const ConvParams& p, cudaStream_t stream);
+int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int N, int C, int H, int W, int Ho, int Wo, float slope, float* z,
+                     cudaStream_t stream);
+int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);
+int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
+                int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
+                float* out, float* pyramid, cudaStream_t stream);
+
+}  // namespace kbnet

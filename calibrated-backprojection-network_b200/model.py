@@ -1,0 +1,271 @@
+"""The callers either side of the hot path, re-built for inference on B200.
+
+  * KBNetEncoder       mirrors networks.KBNetEncoder        (reference src/networks.py:24-533)
+  * MultiScaleDecoder  mirrors networks.MultiScaleDecoder   (reference src/networks.py:1605-1989; n_resolution=1, 'up')
+  * KBNetModel         mirrors kbnet_model.KBNetModel       (reference src/kbnet_model.py:63-186, 378-406)
+
+Parameter trees (state_dict keys / shapes) are identical to the reference so ``kbnet-*.pth`` checkpoints load.
+Differences by design: no torch.nn.DataParallel (one process per GPU, see dist.py); K^-1 goes to the KB kernels
+as 9 floats per sample instead of an [N,3,H,W] coordinates tensor; skip concatenations are written in place.
+"""
+import torch
+
+from . import ops
+from .modules import (CalibratedBackprojectionBlock, ConvBlockWeight, ConvWeight, SparseToDensePool, activation_slope)
+
+# Backend of the convolutions that are NOT on the north-star hot path (conv0_*, conv5_*, decoder):
+#   'kbnet' -> this library's fused conv (kbnet_conv2d_forward);  'torch' -> stock cuDNN (the incumbent, for A/B runs).
+CONV_BACKEND = 'kbnet'
+
+
+def _conv(sources, weight, stride, slope, out=None):
+    if CONV_BACKEND == 'kbnet':
+        return ops.conv2d_fused(sources, weight, stride, slope, out)
+    import torch.nn.functional as F
+    size = None
+    for s in sources:
+        if not isinstance(s, (tuple, list)):
+            size = tuple(s.shape[-2:])
+    parts = []
+    for s in sources:
+        if isinstance(s, (tuple, list)):
+            parts.append(F.interpolate(s[0], size=size if size is not None else tuple(s[2]), mode='nearest'))
+        else:
+            parts.append(s)
+    x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        y = F.conv2d(x, weight, None, stride=stride, padding=weight.shape[-1] // 2)
+    if slope is not None:
+        y = F.leaky_relu(y, slope, inplace=True)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+class KBNetEncoder(torch.nn.Module):
+    """reference src/networks.py:24-533 with KB layers at resolutions [0,1,2,3] (the only configuration KBNet ships)."""
+
+    def __init__(self,
+                 input_channels_image=3,
+                 input_channels_depth=1,
+                 n_filters_image=[48, 96, 192, 384, 384],
+                 n_filters_depth=[16, 32, 64, 128, 128],
+                 n_filters_fused=[48, 96, 192, 384, 384],
+                 n_convolutions_image=[1, 1, 1, 1, 1],
+                 n_convolutions_depth=[1, 1, 1, 1, 1],
+                 n_convolutions_fused=[1, 1, 1, 1, 1],
+                 resolutions_backprojection=[0, 1, 2],
+                 weight_initializer='kaiming_uniform',
+                 activation_func='leaky_relu'):
+        super().__init__()
+        if sorted(resolutions_backprojection) != [0, 1, 2, 3]:
+            raise NotImplementedError('kbnet_b200: KBNetEncoder supports resolutions_backprojection=[0,1,2,3] '
+                                      '(every shipped KBNet configuration); got %r' % (resolutions_backprojection,))
+        for lst in (n_filters_image, n_filters_depth, n_filters_fused, n_convolutions_image, n_convolutions_depth,
+                    n_convolutions_fused):
+            assert len(lst) == 5
+        self.negative_slope = activation_slope(activation_func)
+        act = torch.nn.LeakyReLU(negative_slope=self.negative_slope, inplace=True)
+        fi, fd, ff = n_filters_image, n_filters_depth, n_filters_fused
+        self.n_filters_image, self.n_filters_depth, self.n_filters_fused = list(fi), list(fd), list(ff)
+        self.conv0_image = ConvWeight(input_channels_image, fi[0], 3, 1, weight_initializer)
+        self.conv0_depth = ConvWeight(input_channels_depth, fd[0], 3, 1, weight_initializer)
+        c_img, c_dep, c_fus = fi[0], fd[0], fi[0]
+        for n in range(4):
+            blk = CalibratedBackprojectionBlock(c_img, c_dep, c_fus, fi[n], fd[n], ff[n],
+                                                n_convolutions_image[n], n_convolutions_depth[n], n_convolutions_fused[n],
+                                                weight_initializer, act)
+            setattr(self, 'calibrated_backprojection%d' % (n + 1), blk)
+            c_img, c_dep = fi[n], fd[n]
+            c_fus = fi[n] + ff[n]                                     # src/networks.py:142,184,226
+        self.conv5_image = ConvBlockWeight(ff[3], fi[4], n_convolutions_image[4], 2, weight_initializer)
+        self.conv5_depth = ConvBlockWeight(fd[3], fd[4], n_convolutions_depth[4], 2, weight_initializer)
+
+    @staticmethod
+    def inverse_intrinsics(intrinsics, h0, w0, h1, w1):
+        """K^-1 for level 0 and for levels 1..3.  The reference's scale_intrinsics closure (src/networks.py:333-352)
+        always applies the level-1/level-0 ratio, whatever level it is called for; pretrained weights depend on that,
+        so it is reproduced: levels 1, 2 and 3 share K * [[sx,1,sx],[1,sy,sy],[1,1,1]], sx = W1/W0, sy = H1/H0."""
+        sx, sy = w1 / w0, h1 / h0
+        scale = torch.tensor([[sx, 1.0, sx], [1.0, sy, sy], [1.0, 1.0, 1.0]], dtype=torch.float32, device=intrinsics.device)
+        return torch.inverse(intrinsics).contiguous(), torch.inverse(intrinsics * scale.view(1, 3, 3)).contiguous()
+
+    def forward(self, image, depth, intrinsics):
+        slope = self.negative_slope
+        n, _, h0, w0 = image.shape
+        dev = image.device
+        h1, w1 = (h0 - 1) // 2 + 1, (w0 - 1) // 2 + 1
+        kinv0, kinv1 = self.inverse_intrinsics(intrinsics, h0, w0, h1, w1)
+        conv_image = _conv([image], self.conv0_image.weight, 1, slope)                   # src/networks.py:364
+        conv_depth = _conv([depth], self.conv0_depth.weight, 1, slope)                   # :365
+        conv_fused = None
+        skips = []
+        h, w = h0, w0
+        for lvl in range(4):
+            blk = getattr(self, 'calibrated_backprojection%d' % (lvl + 1))
+            ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            f_f, f_d = blk.n_filter_fused, blk.n_filter_depth
+            skip = torch.empty((n, f_f + f_d, ho, wo), dtype=torch.float32, device=dev)   # cat([fused, depth]) in place
+            conv_image, conv_depth, conv_fused = blk(image=conv_image, depth=conv_depth,
+                                                     coordinates=kinv0 if lvl == 0 else kinv1, fused=conv_fused,
+                                                     out_fused=skip[:, :f_f], out_depth=skip[:, f_f:])
+            skips.append(skip)
+            h, w = ho, wo
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        f5i, f5d = self.conv5_image.weight.shape[0], self.conv5_depth.weight.shape[0]
+        latent = torch.empty((n, f5i + f5d, ho, wo), dtype=torch.float32, device=dev)
+        _conv([conv_fused], self.conv5_image.weight, 2, slope, out=latent[:, :f5i])      # :520-523 (input = conv4_fused)
+        _conv([conv_depth], self.conv5_depth.weight, 2, slope, out=latent[:, f5i:])      # :527
+        return latent, skips
+
+
+class _UpConvWeight(torch.nn.Module):        # key: deconv.conv.conv.weight  (UpConv2d.conv = Conv2d)
+    def __init__(self, cin, cout, init):
+        super().__init__()
+        self.conv = ConvWeight(cin, cout, 3, 1, init)
+
+
+class DecoderBlock(torch.nn.Module):
+    """reference src/net_utils.py:1377-1487 with deconv_type='up'."""
+
+    def __init__(self, in_channels, skip_channels, out_channels, weight_initializer='kaiming_uniform'):
+        super().__init__()
+        self.skip_channels = skip_channels
+        self.deconv = _UpConvWeight(in_channels, out_channels, weight_initializer)
+        self.conv = ConvWeight(skip_channels + out_channels, out_channels, 3, 1, weight_initializer)
+
+    def forward(self, x, skip, shape, slope):
+        size = tuple(skip.shape[-2:]) if skip is not None else tuple(shape)
+        d = _conv([(x, 'up', size)], self.deconv.conv.weight, 1, slope)                   # nearest-up + conv fused
+        srcs = [d, skip] if self.skip_channels > 0 else [d]
+        return _conv(srcs, self.conv.weight, 1, slope)                                    # cat([deconv, skip]) fused
+
+
+class MultiScaleDecoder(torch.nn.Module):
+    """reference src/networks.py:1605-1989 for the KBNet configuration: n_resolution=1, deconv_type='up',
+    output_func='linear', 5 decoder blocks."""
+
+    def __init__(self, input_channels=256, output_channels=1, n_resolution=4, n_filters=[256, 128, 64, 32, 16],
+                 n_skips=[256, 128, 64, 32, 0], weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+                 output_func='linear', use_batch_norm=False, use_instance_norm=False, deconv_type='transpose'):
+        super().__init__()
+        if n_resolution != 1 or deconv_type != 'up' or output_func != 'linear' or use_batch_norm or use_instance_norm \
+                or len(n_filters) != 5:
+            raise NotImplementedError('kbnet_b200: MultiScaleDecoder supports the KBNet configuration only '
+                                      '(n_resolution=1, deconv_type="up", output_func="linear", 5 levels, no norm)')
+        self.negative_slope = activation_slope(activation_func)
+        c = input_channels
+        for i, name in enumerate(('deconv4', 'deconv3', 'deconv2', 'deconv1', 'deconv0')):
+            setattr(self, name, DecoderBlock(c, n_skips[i], n_filters[i], weight_initializer))
+            c = n_filters[i]
+        self.output0 = ConvWeight(c, output_channels, 3, 1, weight_initializer)
+
+    def forward(self, x, skips, shape=None):
+        slope = self.negative_slope
+        x = self.deconv4(x, skips[3], None, slope)
+        x = self.deconv3(x, skips[2], None, slope)
+        x = self.deconv2(x, skips[1], None, slope)
+        x = self.deconv1(x, skips[0], None, slope)
+        x = self.deconv0(x, None, shape, slope)
+        return [_conv([x], self.output0.weight, 1, None)]
+
+
+class KBNetModel(object):
+    """Inference mirror of kbnet_model.KBNetModel (reference src/kbnet_model.py:63-186, 378-406).
+    Same constructor arguments and ``forward(image, sparse_depth, validity_map_depth, intrinsics)``."""
+
+    def __init__(self,
+                 input_channels_image,
+                 input_channels_depth,
+                 min_pool_sizes_sparse_to_dense_pool,
+                 max_pool_sizes_sparse_to_dense_pool,
+                 n_convolution_sparse_to_dense_pool,
+                 n_filter_sparse_to_dense_pool,
+                 n_filters_encoder_image,
+                 n_filters_encoder_depth,
+                 resolutions_backprojection,
+                 n_filters_decoder,
+                 deconv_type='up',
+                 weight_initializer='xavier_normal',
+                 activation_func='leaky_relu',
+                 min_predict_depth=1.5,
+                 max_predict_depth=100.0,
+                 device=torch.device('cuda')):
+        self.min_predict_depth = min_predict_depth
+        self.max_predict_depth = max_predict_depth
+        self.device = device
+        self.sparse_to_dense_pool = SparseToDensePool(
+            input_channels=input_channels_depth,
+            min_pool_sizes=min_pool_sizes_sparse_to_dense_pool,
+            max_pool_sizes=max_pool_sizes_sparse_to_dense_pool,
+            n_convolution=n_convolution_sparse_to_dense_pool,
+            n_filter=n_filter_sparse_to_dense_pool,
+            weight_initializer=weight_initializer,
+            activation_func=activation_func)
+        n_filters_encoder = [i + z for i, z in zip(n_filters_encoder_image, n_filters_encoder_depth)]
+        n_skips = n_filters_encoder[:-1][::-1] + [0]
+        self.encoder = KBNetEncoder(
+            input_channels_image=input_channels_image,
+            input_channels_depth=n_filter_sparse_to_dense_pool,
+            n_filters_image=n_filters_encoder_image,
+            n_filters_depth=n_filters_encoder_depth,
+            n_filters_fused=list(n_filters_encoder_image),
+            resolutions_backprojection=resolutions_backprojection,
+            weight_initializer=weight_initializer,
+            activation_func=activation_func)
+        self.decoder = MultiScaleDecoder(
+            input_channels=n_filters_encoder[-1], output_channels=1, n_resolution=1, n_filters=n_filters_decoder,
+            n_skips=n_skips, weight_initializer=weight_initializer, activation_func=activation_func,
+            output_func='linear', use_batch_norm=False, deconv_type=deconv_type)
+        self.to(self.device)
+        self.eval()
+
+    # -- reference-compatible plumbing ------------------------------------------------------------------
+    def modules(self):
+        return (self.sparse_to_dense_pool, self.encoder, self.decoder)
+
+    def to(self, device):
+        self.device = device
+        for m in self.modules():
+            m.to(device)
+
+    def eval(self):
+        for m in self.modules():
+            m.eval()
+
+    def parameters(self):
+        return [p for m in self.modules() for p in m.parameters()]
+
+    def load_state_dicts(self, s2d_sd, enc_sd, dec_sd):
+        strip = lambda sd: {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}  # DataParallel prefix
+        self.sparse_to_dense_pool.load_state_dict(strip(s2d_sd), strict=True)
+        self.encoder.load_state_dict(strip(enc_sd), strict=True)
+        self.decoder.load_state_dict(strip(dec_sd), strict=True)
+
+    def restore_model(self, checkpoint_path, optimizer=None):
+        """Loads a reference checkpoint (src/kbnet_model.py:378-406): keys 'sparse_to_dense_pool_state_dict',
+        'encoder_state_dict', 'decoder_state_dict' (each 'module.'-prefixed), 'train_step'."""
+        ckpt = torch.load(checkpoint_path, map_location=self.device)
+        self.load_state_dicts(ckpt['sparse_to_dense_pool_state_dict'], ckpt['encoder_state_dict'], ckpt['decoder_state_dict'])
+        return ckpt.get('train_step', 0), optimizer
+
+    def save_model(self, checkpoint_path, step=0):
+        """Writes the reference checkpoint layout (src/kbnet_model.py:353-376) so the reference can load it back."""
+        pre = lambda sd: {'module.' + k: v for k, v in sd.items()}
+        torch.save({'train_step': step,
+                    'sparse_to_dense_pool_state_dict': pre(self.sparse_to_dense_pool.state_dict()),
+                    'encoder_state_dict': pre(self.encoder.state_dict()),
+                    'decoder_state_dict': pre(self.decoder.state_dict())}, checkpoint_path)
+
+    # -- forward ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, image, sparse_depth, validity_map_depth, intrinsics):
+        input_depth = torch.cat([sparse_depth, validity_map_depth], dim=1)             # src/kbnet_model.py:166-171
+        input_depth = self.sparse_to_dense_pool(input_depth)                           # :173
+        shape = input_depth.shape[-2:]
+        latent, skips = self.encoder(image, input_depth, intrinsics)                   # :177
+        output = self.decoder(latent, skips, shape)[-1]                                # :179
+        return ops.depth_head(output, self.min_predict_depth, self.max_predict_depth)  # :181-184
+
+    __call__ = forward

@@ -1,0 +1,291 @@
+"""Drop-in torch.nn.Module mirrors of the reference's two hot-path layers, backed by libkbnet_b200.so.
+
+Same constructor / forward signatures and the same parameter tree (state_dict keys and shapes) as
+
+  * networks.SparseToDensePool              reference src/networks.py:2078-2196
+  * net_utils.CalibratedBackprojectionBlock reference src/net_utils.py:1269-1371
+
+so the reference's kbnet_model.py runs unchanged after ``kbnet_b200.install()`` and its checkpoints load with
+``strict=True``.  Forward is inference-only and CUDA-only: anything else raises (there is no CPU fallback).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter containers reproducing the reference key names
+# ---------------------------------------------------------------------------------------------------------
+def activation_slope(activation_func):
+    """Map the reference's activation spec (net_utils.activation_func, src/net_utils.py:23-45; a string for S2D,
+    an nn.Module instance for the KB block) to the negative slope the kernels apply."""
+    if activation_func is None:
+        raise NotImplementedError('kbnet_b200: linear (no) activation is not part of the hot path')
+    if isinstance(activation_func, str):
+        if 'linear' in activation_func:
+            raise NotImplementedError('kbnet_b200: linear (no) activation is not part of the hot path')
+        if 'leaky_relu' in activation_func:
+            return 0.20  # src/net_utils.py:37
+        if 'relu' in activation_func:
+            return 0.0
+        if 'elu' in activation_func or 'sigmoid' in activation_func:
+            raise NotImplementedError('kbnet_b200: activation %r has no sm_100a kernel' % activation_func)
+        raise ValueError('Unsupported activation function: {}'.format(activation_func))  # src/net_utils.py:45
+    if isinstance(activation_func, torch.nn.LeakyReLU):
+        return float(activation_func.negative_slope)
+    if isinstance(activation_func, torch.nn.ReLU):
+        return 0.0
+    raise NotImplementedError('kbnet_b200: activation %r has no sm_100a kernel' % (activation_func,))
+
+
+def _init_weight(weight, weight_initializer):
+    # src/net_utils.py:95-105
+    if weight_initializer == 'kaiming_normal':
+        torch.nn.init.kaiming_normal_(weight)
+    elif weight_initializer == 'xavier_normal':
+        torch.nn.init.xavier_normal_(weight)
+    elif weight_initializer == 'xavier_uniform':
+        torch.nn.init.xavier_uniform_(weight)
+    elif weight_initializer == 'kaiming_uniform':
+        pass
+    else:
+        raise ValueError('Unsupported weight initializer: {}'.format(weight_initializer))
+
+
+class ConvWeight(torch.nn.Module):
+    """Holds ``conv.weight`` [out, in, k, k] exactly like net_utils.Conv2d (bias-free, src/net_utils.py:87-93)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, weight_initializer='kaiming_uniform'):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                                    padding=kernel_size // 2, bias=False)
+        _init_weight(self.conv.weight, weight_initializer)
+        self.kernel_size = kernel_size
+        self.stride = stride
+
+    @property
+    def weight(self):
+        return self.conv.weight
+
+
+class ConvBlockWeight(torch.nn.Module):
+    """Key layout of net_utils.VGGNetBlock with n_convolution == 1: ``conv_block.0.conv.weight``."""
+
+    def __init__(self, in_channels, out_channels, n_convolution=1, stride=1, weight_initializer='kaiming_uniform'):
+        super().__init__()
+        if n_convolution != 1:
+            raise NotImplementedError('kbnet_b200: n_convolution=%d (KBNet always uses 1, src/kbnet_model.py:107-109)'
+                                      % n_convolution)
+        self.conv_block = torch.nn.Sequential(ConvWeight(in_channels, out_channels, 3, stride, weight_initializer))
+
+    @property
+    def weight(self):
+        return self.conv_block[0].conv.weight
+
+
+def _check_input(name, t, ndim=4):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('kbnet_b200: %s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise RuntimeError('kbnet_b200: %s is on %s; this path runs on CUDA (sm_100a) only, there is no CPU fallback'
+                           % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError('kbnet_b200: %s must be float32 (got %s)' % (name, t.dtype))
+    if t.dim() != ndim:
+        raise RuntimeError('kbnet_b200: %s must be %d-D (got shape %s)' % (name, ndim, tuple(t.shape)))
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError('kbnet_b200: inference-only kernels; call under torch.no_grad() (no backward is provided)')
+    return t.contiguous()
+
+
+def _view4(name, t):
+    """Validate a 4-D input and return (tensor, elements-between-samples).  A channel slice of a wider NCHW buffer
+    (dense C,H,W strides, larger batch stride) is passed through without a copy."""
+    if isinstance(t, torch.Tensor) and t.dim() == 4 and t.is_cuda and t.dtype == torch.float32:
+        c, h, w = t.shape[1:]
+        if t.stride()[1:] == (h * w, w, 1) and (t.shape[0] == 1 or t.stride(0) >= c * h * w):
+            if torch.is_grad_enabled() and t.requires_grad:
+                raise RuntimeError('kbnet_b200: inference-only kernels; call under torch.no_grad()')
+            return t, (t.stride(0) if t.shape[0] > 1 else c * h * w)
+    t = _check_input(name, t)
+    return t, t.shape[1] * t.shape[2] * t.shape[3]
+
+
+def _w(param, device):
+    w = param.detach()
+    if w.device != device:
+        raise RuntimeError('kbnet_b200: weights on %s but input on %s' % (w.device, device))
+    return w.contiguous()
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SparseToDensePool
+# ---------------------------------------------------------------------------------------------------------
+class SparseToDensePool(torch.nn.Module):
+    """Mirror of networks.SparseToDensePool (reference src/networks.py:2078-2196): one fused sm_100a kernel."""
+
+    def __init__(self,
+                 input_channels,
+                 min_pool_sizes=[3, 5, 7, 9],
+                 max_pool_sizes=[3, 5, 7, 9],
+                 n_filter=8,
+                 n_convolution=3,
+                 weight_initializer='kaiming_uniform',
+                 activation_func='leaky_relu'):
+        super().__init__()
+        self.negative_slope = activation_slope(activation_func)
+        self.min_pool_sizes = [s for s in min_pool_sizes if s > 1]   # src/networks.py:2112-2118
+        self.max_pool_sizes = [s for s in max_pool_sizes if s > 1]
+        self.len_pool_sizes = len(self.min_pool_sizes) + len(self.max_pool_sizes)
+        self.input_channels = input_channels
+        self.n_filter = n_filter
+        self.n_convolution = n_convolution
+        in_channels = self.len_pool_sizes
+        pool_convs = []
+        for _ in range(n_convolution):
+            pool_convs.append(ConvWeight(in_channels, n_filter, 1, 1, weight_initializer))
+            in_channels = n_filter
+        self.pool_convs = torch.nn.Sequential(*pool_convs)
+        self.conv = ConvWeight(n_filter + input_channels, n_filter, 3, 1, weight_initializer)
+
+    def forward(self, x, return_pyramid=False):
+        x = _check_input('x', x)
+        for s in self.min_pool_sizes + self.max_pool_sizes:
+            if s % 2 == 0:
+                # the reference fails at the torch.cat in src/networks.py:2194 (H+1 rows); fail the same way, earlier
+                raise RuntimeError('kbnet_b200: even pool size %d changes the spatial size (reference raises in torch.cat)' % s)
+        n, c, h, w = x.shape
+        if c != self.input_channels:
+            raise RuntimeError('kbnet_b200: expected %d input channels, got %d' % (self.input_channels, c))
+        lib = _lib.load()
+        dev = x.device
+        out = torch.empty((n, self.n_filter, h, w), dtype=torch.float32, device=dev)
+        pyr = torch.empty((n, self.len_pool_sizes, h, w), dtype=torch.float32, device=dev) if return_pyramid else None
+        w1 = [_w(m.conv.weight, dev) for m in self.pool_convs]
+        w3 = _w(self.conv.conv.weight, dev)
+        n_min, n_max = len(self.min_pool_sizes), len(self.max_pool_sizes)
+        mins = (ctypes.c_int * max(n_min, 1))(*self.min_pool_sizes)
+        maxs = (ctypes.c_int * max(n_max, 1))(*self.max_pool_sizes)
+        w1p = (ctypes.c_void_p * max(len(w1), 1))(*[t.data_ptr() for t in w1])
+        with torch.cuda.device(dev):
+            rc = lib.kbnet_s2d_forward(x.data_ptr(), n, c, h, w, mins, n_min, maxs, n_max, w1p, len(w1), self.n_filter,
+                                       w3.data_ptr(), self.negative_slope, out.data_ptr(),
+                                       pyr.data_ptr() if pyr is not None else None, _stream(dev))
+        _lib.check(rc, 'kbnet_s2d_forward')
+        return (out, pyr) if return_pyramid else out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CalibratedBackprojectionBlock
+# ---------------------------------------------------------------------------------------------------------
+class CalibratedBackprojectionBlock(torch.nn.Module):
+    """Mirror of net_utils.CalibratedBackprojectionBlock (reference src/net_utils.py:1269-1371).
+
+    ``forward(image, depth, coordinates, fused=None)`` accepts what the reference passes.  In addition
+    ``coordinates`` may be an ``[N, 3, 3]`` tensor holding K^-1 per sample: the kernels then generate the
+    per-pixel coordinates themselves and the [N,3,H,W] tensor never exists (fast path used by KBNetEncoder here).
+    """
+
+    def __init__(self,
+                 in_channels_image,
+                 in_channels_depth,
+                 in_channels_fused,
+                 n_filter_image=48,
+                 n_filter_depth=16,
+                 n_filter_fused=48,
+                 n_convolution_image=1,
+                 n_convolution_depth=1,
+                 n_convolution_fused=1,
+                 weight_initializer='kaiming_uniform',
+                 activation_func=torch.nn.LeakyReLU(negative_slope=0.10, inplace=True)):
+        super().__init__()
+        self.negative_slope = activation_slope(activation_func)
+        self.in_channels_image = in_channels_image
+        self.in_channels_depth = in_channels_depth
+        self.in_channels_fused = in_channels_fused  # already includes the image channels (src/networks.py:102,142)
+        self.n_filter_image, self.n_filter_depth, self.n_filter_fused = n_filter_image, n_filter_depth, n_filter_fused
+        self.conv_image = ConvBlockWeight(in_channels_image, n_filter_image, n_convolution_image, 2, weight_initializer)
+        self.conv_depth = ConvBlockWeight(in_channels_depth + 3, n_filter_depth, n_convolution_depth, 2, weight_initializer)
+        self.proj_depth = ConvWeight(in_channels_depth, 1, 1, 1, weight_initializer)
+        # n_convolution_fused is ignored by the reference too (src/net_utils.py:1335-1341)
+        self.conv_fused = ConvWeight(in_channels_fused + 3, n_filter_fused, 1, 2, weight_initializer)
+
+    def forward(self, image, depth, coordinates, fused=None, out_image=None, out_depth=None, out_fused=None):
+        image, image_sn = _view4('image', image)
+        depth, depth_sn = _view4('depth', depth)
+        n, c_i, h, w = image.shape
+        c_d = depth.shape[1]
+        dev = image.device
+        if depth.shape[0] != n or tuple(depth.shape[-2:]) != (h, w):
+            raise RuntimeError('kbnet_b200: depth shape %s does not match image %s' % (tuple(depth.shape), tuple(image.shape)))
+        c_f, fused_sn = 0, 0
+        if fused is not None:
+            fused, fused_sn = _view4('fused', fused)
+            c_f = fused.shape[1]
+            if fused.shape[0] != n or tuple(fused.shape[-2:]) != (h, w):
+                raise RuntimeError('kbnet_b200: fused shape %s does not match image' % (tuple(fused.shape),))
+        if c_i != self.in_channels_image or c_d != self.in_channels_depth or c_i + c_f != self.in_channels_fused:
+            raise RuntimeError('kbnet_b200: channel mismatch: image %d (expected %d), depth %d (expected %d), '
+                               'image+fused %d (expected %d)' % (c_i, self.in_channels_image, c_d, self.in_channels_depth,
+                                                                c_i + c_f, self.in_channels_fused))
+        coords_ptr = kinv_ptr = None
+        if coordinates.dim() == 3:
+            kinv = _check_input('coordinates (K^-1)', coordinates, 3)
+            if tuple(kinv.shape) != (n, 3, 3):
+                raise RuntimeError('kbnet_b200: K^-1 must be [N,3,3], got %s' % (tuple(kinv.shape),))
+            kinv_ptr = kinv.data_ptr()
+        else:
+            coordinates = _check_input('coordinates', coordinates)
+            if tuple(coordinates.shape) != (n, 3, h, w):
+                raise RuntimeError('kbnet_b200: coordinates must be [N,3,H,W], got %s' % (tuple(coordinates.shape),))
+            coords_ptr = coordinates.data_ptr()
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        f_i, f_d, f_f = self.n_filter_image, self.n_filter_depth, self.n_filter_fused
+
+        def _out(t, f):
+            if t is None:
+                return torch.empty((n, f, ho, wo), dtype=torch.float32, device=dev)
+            # a channel slice of a wider [N, C, ho, wo] buffer (lets the encoder skip the torch.cat of the skips)
+            if tuple(t.shape) != (n, f, ho, wo) or t.dtype != torch.float32 or t.device != dev or \
+                    t.stride()[1:] != (ho * wo, wo, 1):
+                raise RuntimeError('kbnet_b200: preallocated output must be a [N,%d,%d,%d] float32 channel slice' % (f, ho, wo))
+            return t
+
+        o_i, o_d, o_f = _out(out_image, f_i), _out(out_depth, f_d), _out(out_fused, f_f)
+        lib = _lib.load()
+        ws_bytes = lib.kbnet_kb_workspace_bytes(n, c_i, c_d, c_f, h, w, f_i, f_d, f_f)
+        ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=dev)
+        wi, wd = _w(self.conv_image.weight, dev), _w(self.conv_depth.weight, dev)
+        wp, wf = _w(self.proj_depth.weight, dev), _w(self.conv_fused.weight, dev)
+        sn = lambda t: t.stride(0) if n > 1 else t.shape[1] * ho * wo
+        with torch.cuda.device(dev):
+            rc = lib.kbnet_kb_forward(image.data_ptr(), image_sn, depth.data_ptr(), depth_sn,
+                                      fused.data_ptr() if fused is not None else None, fused_sn, coords_ptr, kinv_ptr, n, c_i, c_d, c_f, h, w,
+                                      wi.data_ptr(), f_i, wd.data_ptr(), f_d, wp.data_ptr(), wf.data_ptr(), f_f,
+                                      self.negative_slope,
+                                      o_i.data_ptr(), sn(o_i), o_d.data_ptr(), sn(o_d), o_f.data_ptr(), sn(o_f),
+                                      ws.data_ptr(), ws_bytes, _stream(dev))
+        _lib.check(rc, 'kbnet_kb_forward')
+        return o_i, o_d, o_f
+
+
+# ---------------------------------------------------------------------------------------------------------
+# install(): swap the two classes into the reference's flat modules
+# ---------------------------------------------------------------------------------------------------------
+def install(networks_module=None, net_utils_module=None):
+    """Monkey-patch ``networks.SparseToDensePool`` and ``net_utils.CalibratedBackprojectionBlock`` (the reference
+    resolves them by flat module name: src/kbnet_model.py:18,87; src/networks.py:18,104) so that
+    ``kbnet_model.KBNetModel(...)`` builds the B200 layers.  Returns the originals for un-patching."""
+    import importlib
+    networks_module = networks_module or importlib.import_module('networks')
+    net_utils_module = net_utils_module or importlib.import_module('net_utils')
+    originals = (networks_module.SparseToDensePool, net_utils_module.CalibratedBackprojectionBlock)
+    networks_module.SparseToDensePool = SparseToDensePool
+    net_utils_module.CalibratedBackprojectionBlock = CalibratedBackprojectionBlock
+    return originals

@@ -1,0 +1,67 @@
+"""Functional wrappers over the C ABI for the convolutions either side of the hot path."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .modules import _view4, _w, _stream
+
+
+def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None):
+    """out = act(conv_k(cat_c(sources), weight)), padding k//2, no bias.
+
+    sources: list of 4-D CUDA float32 tensors or ``(tensor, 'up')`` pairs; an ``'up'`` source is nearest-upsampled to
+    the spatial size of the first non-upsampled source (or ``size`` given as ``(tensor, 'up', (H, W))``) inside the kernel.
+    slope=None means no activation.  ``out`` may be a channel slice of a wider NCHW buffer.
+    Replaces Conv2d.forward + torch.cat + F.interpolate(mode='nearest') of the reference
+    (src/net_utils.py:120-141, 484-499, 1453-1487; src/networks.py:364-365, 520-531).
+    """
+    lib = _lib.load()
+    parsed, h_in, w_in = [], None, None
+    for s in sources:
+        if isinstance(s, (tuple, list)):
+            t, sn = _view4('source', s[0])
+            parsed.append((t, sn, 1))
+            if len(s) > 2 and h_in is None:
+                h_in, w_in = int(s[2][0]), int(s[2][1])
+        else:
+            t, sn = _view4('source', s)
+            parsed.append((t, sn, 0))
+            h_in, w_in = t.shape[2], t.shape[3]
+    if h_in is None:
+        raise RuntimeError('kbnet_b200: conv2d_fused needs a size for upsample-only inputs')
+    dev = parsed[0][0].device
+    n = parsed[0][0].shape[0]
+    w = _w(weight, dev)
+    f, ctot, k, _ = w.shape
+    if sum(t.shape[1] for t, _, _ in parsed) != ctot:
+        raise RuntimeError('kbnet_b200: conv weight expects %d input channels, sources have %d'
+                           % (ctot, sum(t.shape[1] for t, _, _ in parsed)))
+    pad = k // 2
+    ho, wo = (h_in + 2 * pad - k) // stride + 1, (w_in + 2 * pad - k) // stride + 1
+    if out is None:
+        out = torch.empty((n, f, ho, wo), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, f, ho, wo) or out.stride()[1:] != (ho * wo, wo, 1) or out.dtype != torch.float32:
+        raise RuntimeError('kbnet_b200: bad preallocated conv output')
+    arr = (_lib.KBNetConvSrc * len(parsed))()
+    for i, (t, sn, mode) in enumerate(parsed):
+        arr[i].ptr, arr[i].C, arr[i].H, arr[i].W, arr[i].stride_n, arr[i].mode = t.data_ptr(), t.shape[1], t.shape[2], t.shape[3], sn, mode
+    osn = out.stride(0) if n > 1 else f * ho * wo
+    with torch.cuda.device(dev):
+        rc = lib.kbnet_conv2d_forward(arr, len(parsed), n, h_in, w_in, w.data_ptr(), f, k, stride,
+                                      0 if slope is None else 1, 0.0 if slope is None else float(slope),
+                                      out.data_ptr(), osn, _stream(dev))
+    _lib.check(rc, 'kbnet_conv2d_forward')
+    return out
+
+
+def depth_head(x, min_predict_depth, max_predict_depth):
+    """min_d / (sigmoid(x) + min_d / max_d)   (reference src/kbnet_model.py:181-184)."""
+    lib = _lib.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.kbnet_depth_head_forward(x.data_ptr(), x.numel(), float(min_predict_depth), float(max_predict_depth),
+                                          y.data_ptr(), _stream(x.device))
+    _lib.check(rc, 'kbnet_depth_head_forward')
+    return y

@@ -1,0 +1,123 @@
+/*
+ * kbnet_b200.h -- C ABI of libkbnet_b200.so: B200 (sm_100a) kernels for KBNet's geometric hot path.
+ *
+ * The reference (alexklwong/calibrated-backprojection-network) is pure Python/PyTorch and has no FFI;
+ * its "operator interface" for this path is two torch.nn.Module classes.  The entry points below are
+ * what a ctypes binding for those two modules (and for the convolutions either side of them) binds;
+ * each cites the reference code it replaces.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - all tensors are contiguous NCHW float32 DEVICE pointers unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is
+ *     asynchronous with respect to the host (no host synchronisation inside);
+ *   - the device is the CURRENT device of the calling thread (caller does cudaSetDevice / torch.cuda.device);
+ *   - return value: 0 on success, non-zero on failure (cudaError_t value, or KBNET_E_* below);
+ *     kbnet_last_error() returns a thread-local message for the last failure on this thread;
+ *   - no global mutable state: safe to call concurrently from several host threads / streams
+ *     (torch.nn.DataParallel replicas call forward from one thread per device).
+ */
+#ifndef KBNET_B200_H_
+#define KBNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBNET_B200_VERSION 100 /* 0.1.0 */
+
+#define KBNET_E_BADARG      10001 /* invalid argument / unsupported configuration (message says which) */
+#define KBNET_E_WORKSPACE   10002 /* workspace too small */
+#define KBNET_E_ALIGN       10003 /* pointer not 16-byte aligned where required */
+
+int         kbnet_version(void);
+const char* kbnet_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (statistics only; monotonically increasing). */
+unsigned long long kbnet_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SparseToDensePool.forward -- replaces reference src/networks.py:2168-2196 (module ctor :2100-2166).
+ *
+ *   z = x[:,0];  pyramid = [minpool_s(z) for s in min_sizes] + [maxpool_s(z) for s in max_sizes]
+ *   q = pyramid; for i < n_conv: q = leaky(conv1x1(q, w_1x1[i]))
+ *   out = leaky(conv3x3_pad1(cat([q, x]), w_3x3))
+ *
+ *   x        [N, C_in, H, W]      input (channel 0 = sparse depth)
+ *   min_sizes/max_sizes           HOST int arrays, odd sizes >= 3 (sizes <= 1 must be dropped by the caller,
+ *                                 as the reference ctor does at :2112-2118); size <= 33
+ *   w_1x1    HOST array of n_conv DEVICE pointers: w_1x1[0] is [n_filter, n_min+n_max], others [n_filter, n_filter]
+ *   w_3x3    [n_filter, n_filter + C_in, 3, 3]
+ *   out      [N, n_filter, H, W]
+ *   pyramid  optional (may be NULL) [N, n_min+n_max, H, W]: the pool pyramid, for bit-exact checks
+ * Supported: n_filter == 8, 1 <= n_conv <= 8, 1 <= n_min+n_max <= 16, 1 <= C_in <= 8.
+ */
+int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W,
+                      const int* min_sizes, int n_min, const int* max_sizes, int n_max,
+                      const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3,
+                      float neg_slope, float* out, float* pyramid, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CalibratedBackprojectionBlock.forward -- replaces reference src/net_utils.py:1343-1371
+ * (ctor :1297-1341), with n_convolution_* == 1 as KBNet always uses (src/kbnet_model.py:107-109).
+ *
+ *   conv_image = leaky(conv3x3_s2_p1(image, w_image))
+ *   conv_depth = leaky(conv3x3_s2_p1(cat([depth, coords]), w_depth))
+ *   z          = leaky(conv1x1(depth, w_proj))            (1 output channel)
+ *   conv_fused = leaky(conv1x1_s2(cat([image, coords * z, fused?]), w_fused))
+ *
+ *   image [N,C_i,H,W]  depth [N,C_d,H,W]  fused [N,C_f,H,W] or NULL (then C_f must be 0); each with its own
+ *   `*_stride_n` = elements between samples (>= C*H*W), so channel slices of wider buffers can be read in place
+ *   coords: EITHER `coordinates` [N,3,H,W] (what the reference passes; KBNetEncoder builds it at
+ *           src/networks.py:317-331) OR, when `coordinates` is NULL, `kinv` [N,9] row-major K^-1 per sample,
+ *           from which coords[c](v,u) = kinv[3c]*u + kinv[3c+1]*v + kinv[3c+2] is generated in-kernel.
+ *   w_image [F_i,C_i,3,3]  w_depth [F_d,C_d+3,3,3]  w_proj [1,C_d,1,1]  w_fused [F_f,C_i+3+C_f,1,1]
+ *   out_* [N,F,Ho,Wo] with Ho = (H-1)/2+1, Wo = (W-1)/2+1.  out_*_stride_n = elements between samples of the
+ *   output (>= F*Ho*Wo; lets the caller write straight into a channel slice of a wider concat buffer).
+ *   workspace: DEVICE scratch of at least kbnet_kb_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);
+
+int kbnet_kb_forward(const float* image, long long image_stride_n,
+                     const float* depth, long long depth_stride_n,
+                     const float* fused, long long fused_stride_n,
+                     const float* coordinates, const float* kinv,
+                     int N, int C_i, int C_d, int C_f, int H, int W,
+                     const float* w_image, int F_i, const float* w_depth, int F_d,
+                     const float* w_proj, const float* w_fused, int F_f, float neg_slope,
+                     float* out_image, long long out_image_stride_n,
+                     float* out_depth, long long out_depth_stride_n,
+                     float* out_fused, long long out_fused_stride_n,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fused convolution -- replaces net_utils.Conv2d.forward (src/net_utils.py:120-141) together with the
+ * torch.cat / nearest-interpolate that feed it in KBNetEncoder.forward (src/networks.py:364-365,520-531),
+ * DecoderBlock.forward / UpConv2d.forward (src/net_utils.py:1453-1487, 484-499).
+ *
+ *   out = act(conv_kxk_stride_pad(k/2)(cat_c([src_0, src_1, ...]), w))
+ *
+ * Each source is an NCHW view: `ptr`, `C` channels, spatial (H, W), `stride_n` elements between samples.
+ * mode 0: source resolution == conv input resolution (H_in, W_in);
+ * mode 1: source is nearest-upsampled to (H_in, W_in) on the fly (torch 'nearest' index rule).
+ */
+typedef struct kbnet_conv_src {
+    const float* ptr;
+    int          C, H, W;
+    long long    stride_n;
+    int          mode;
+} kbnet_conv_src;
+
+int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in,
+                         const float* w, int F, int ksize, int stride,
+                         int act /* 0 none, 1 leaky */, float neg_slope,
+                         float* out, long long out_stride_n, void* stream);
+
+/* Output head of KBNetModel.forward (src/kbnet_model.py:181-184): y = min_d / (sigmoid(x) + min_d / max_d). */
+int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBNET_B200_H_ */

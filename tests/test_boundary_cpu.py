@@ -1,0 +1,156 @@
+"""Host-side checks that need no GPU: the C ABI library loads and exports what include/kbnet_b200.h declares, the
+module mirrors have the reference's signatures and parameter trees, and there is no CPU fallback."""
+import ctypes
+import inspect
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+import kbnet_b200
+from kbnet_b200 import _lib
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, 'include', 'kbnet_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(kbnet_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    kbnet_b200.build_library()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_functions()
+    assert set(names) == set(_lib.EXPORTS)
+    for name in names:
+        assert hasattr(lib, name), name
+    assert _lib.load().kbnet_version() == 100
+
+
+def test_library_is_sm100a_and_has_no_torch_dependency():
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert 'sm_100a' in out
+    ldd = subprocess.run(['ldd', _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert 'torch' not in ldd and 'c10' not in ldd
+
+
+def test_bad_arguments_return_error_codes_not_crashes():
+    lib = _lib.load()
+    rc = lib.kbnet_s2d_forward(None, 1, 2, 8, 8, None, 0, None, 0, None, 1, 8, None, 0.2, None, None, None)
+    assert rc != 0 and b'null' in lib.kbnet_last_error()
+    with pytest.raises(RuntimeError, match='kbnet_b200 .* failed'):
+        _lib.check(rc, 'kbnet_s2d_forward')
+
+
+def _ref_signature_strings():
+    # reference src/networks.py:2100-2107, src/net_utils.py:1297-1308, src/kbnet_model.py:63-82
+    return {
+        'SparseToDensePool': ['input_channels', 'min_pool_sizes', 'max_pool_sizes', 'n_filter', 'n_convolution',
+                              'weight_initializer', 'activation_func'],
+        'CalibratedBackprojectionBlock': ['in_channels_image', 'in_channels_depth', 'in_channels_fused', 'n_filter_image',
+                                          'n_filter_depth', 'n_filter_fused', 'n_convolution_image', 'n_convolution_depth',
+                                          'n_convolution_fused', 'weight_initializer', 'activation_func'],
+    }
+
+
+def test_constructor_signatures_match_reference():
+    for name, params in _ref_signature_strings().items():
+        sig = inspect.signature(getattr(kbnet_b200, name).__init__)
+        assert list(sig.parameters)[1:] == params, name
+    s = inspect.signature(kbnet_b200.SparseToDensePool.__init__).parameters
+    assert s['min_pool_sizes'].default == [3, 5, 7, 9] and s['n_filter'].default == 8 and s['n_convolution'].default == 3
+    assert s['activation_func'].default == 'leaky_relu' and s['weight_initializer'].default == 'kaiming_uniform'
+    k = inspect.signature(kbnet_b200.CalibratedBackprojectionBlock.__init__).parameters
+    assert (k['n_filter_image'].default, k['n_filter_depth'].default, k['n_filter_fused'].default) == (48, 16, 48)
+    f = list(inspect.signature(kbnet_b200.CalibratedBackprojectionBlock.forward).parameters)
+    assert f[1:5] == ['image', 'depth', 'coordinates', 'fused']
+
+
+def test_state_dict_trees_match_reference_fixtures():
+    for c in load_golden('s2d_cases.pt'):
+        m = kbnet_b200.SparseToDensePool(c['x'].shape[1], c['min_pool_sizes'], c['max_pool_sizes'], 8, c['n_convolution'],
+                                         'xavier_normal', 'leaky_relu')
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in c['state_dict'].items()}
+        m.load_state_dict(c['state_dict'], strict=True)
+    for c in load_golden('kb_cases.pt'):
+        ci, cd = c['image'].shape[1], c['depth'].shape[1]
+        cf = c['fused'].shape[1] if c['fused'] is not None else 0
+        fi, fd, ff = c['conv_image'].shape[1], c['conv_depth'].shape[1], c['conv_fused'].shape[1]
+        m = kbnet_b200.CalibratedBackprojectionBlock(ci, cd, ci + cf, fi, fd, ff, 1, 1, 1, 'xavier_normal',
+                                                     torch.nn.LeakyReLU(0.2, inplace=True))
+        m.load_state_dict(c['state_dict'], strict=True)
+        assert m.negative_slope == pytest.approx(0.2)
+    g = load_golden('model_small.pt')
+    model = kbnet_b200.KBNetModel(3, 2, g['min_pool_sizes'], g['max_pool_sizes'], 3, 8, g['f_img'], g['f_dep'], [0, 1, 2, 3],
+                                  g['f_dec'], device=torch.device('cpu'))
+    # the fixture keeps the DataParallel 'module.' prefix list too: strict load must work from reference checkpoints
+    assert all(k.startswith('module.') for k in g['raw_state_dict_keys'])
+    model.load_state_dicts({'module.' + k: v for k, v in g['s2d_state_dict'].items()}, g['enc_state_dict'], g['dec_state_dict'])
+
+
+def test_full_size_parameter_count_is_the_reference_one():
+    model = kbnet_b200.KBNetModel(3, 2, [5, 7, 9, 11, 13], [15, 17], 3, 8, [48, 96, 192, 384, 384], [16, 32, 64, 128, 128],
+                                  [0, 1, 2, 3], [256, 128, 128, 64, 12], device=torch.device('cpu'))
+    assert sum(p.numel() for p in model.parameters()) == 6957780
+
+
+def test_no_cpu_fallback():
+    c = load_golden('s2d_cases.pt')[0]
+    m = kbnet_b200.SparseToDensePool(2, c['min_pool_sizes'], c['max_pool_sizes'], 8, 3, 'xavier_normal', 'leaky_relu')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(c['x'])
+    k = load_golden('kb_cases.pt')[0]
+    blk = kbnet_b200.CalibratedBackprojectionBlock(4, 2, 8, 6, 4, 6, 1, 1, 1, 'xavier_normal', torch.nn.LeakyReLU(0.2))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        blk(k['image'], k['depth'], k['coordinates'], k['fused'])
+
+
+def test_activation_and_initializer_errors_follow_reference():
+    with pytest.raises(ValueError, match='Unsupported activation function'):
+        kbnet_b200.SparseToDensePool(2, activation_func='swish')
+    with pytest.raises(ValueError, match='Unsupported weight initializer'):
+        kbnet_b200.SparseToDensePool(2, weight_initializer='orthogonal')
+    m = kbnet_b200.SparseToDensePool(2, [1, 3, 5], [1, 7])           # sizes <= 1 dropped, src/networks.py:2112-2118
+    assert m.min_pool_sizes == [3, 5] and m.max_pool_sizes == [7] and m.pool_convs[0].conv.weight.shape[1] == 3
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'calibrated-backprojection-network_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in txt.replace('the oracle', '').replace('oracle/', ''), os.path.join(dirpath, f)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='needs the reference checkout (build container only)')
+def test_install_drops_into_reference_kbnet_model():
+    """reference kbnet_model.KBNetModel, unchanged, builds the B200 layers after install() and strict-loads a
+    checkpoint produced by the unpatched reference; forward then refuses to run on CPU (no fallback)."""
+    sys.path.insert(0, '/root/reference/src')
+    for m in ('matplotlib', 'matplotlib.pyplot'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    import networks, net_utils, kbnet_model  # noqa: E401
+    args = (3, 2, [5, 7, 9], [11, 13], 3, 8, [8, 16, 16, 32, 32], [4, 8, 8, 16, 16], [0, 1, 2, 3], [32, 16, 16, 8, 4])
+    kw = dict(deconv_type='up', weight_initializer='xavier_normal', activation_func='leaky_relu', device=torch.device('cpu'))
+    ref = kbnet_model.KBNetModel(*args, **kw)
+    orig = kbnet_b200.install(networks, net_utils)
+    try:
+        new = kbnet_model.KBNetModel(*args, **kw)
+        assert isinstance(new.sparse_to_dense_pool.module, kbnet_b200.SparseToDensePool)
+        assert isinstance(new.encoder.module.calibrated_backprojection3, kbnet_b200.CalibratedBackprojectionBlock)
+        new.sparse_to_dense_pool.load_state_dict(ref.sparse_to_dense_pool.state_dict(), strict=True)
+        new.encoder.load_state_dict(ref.encoder.state_dict(), strict=True)
+        new.decoder.load_state_dict(ref.decoder.state_dict(), strict=True)
+        new.eval()
+        g = load_golden('model_small.pt')
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            new.forward(g['image'], g['sparse_depth'], g['validity_map'], g['intrinsics'])
+    finally:
+        networks.SparseToDensePool, net_utils.CalibratedBackprojectionBlock = orig
