@@ -71,6 +71,7 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
                      long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
                      long long out_fused_stride_n, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (N == 0) return 0;
     KB_CHECK_ARG(image && depth && w_image && w_depth && w_proj && w_fused && out_image && out_depth && out_fused,
                  "kb: null pointer argument");
     KB_CHECK_ARG((coordinates != nullptr) != (kinv != nullptr), "kb: pass exactly one of `coordinates` and `kinv`");
@@ -125,6 +126,7 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
 
 int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in, const float* w, int F, int ksize,
                          int stride, int act, float neg_slope, float* out, long long out_stride_n, void* stream) {
+    if (N == 0) return 0;
     KB_CHECK_ARG(srcs && w && out, "conv: null pointer argument");
     KB_CHECK_ARG(n_src >= 1 && n_src <= CONV_MAX_SRC, "conv: n_src=%d unsupported (1..%d)", n_src, CONV_MAX_SRC);
     KB_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "conv: ksize=%d stride=%d unsupported", ksize, stride);

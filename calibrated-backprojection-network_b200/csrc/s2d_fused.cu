@@ -357,6 +357,7 @@ static int launch_s2d(S2DParams& p, cudaStream_t stream) {
 int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
                 int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
                 float* out, float* pyramid, cudaStream_t stream) {
+    if (N == 0) return 0;
     KB_CHECK_ARG(x && out && w_3x3 && w_1x1, "s2d: null pointer argument");
     KB_CHECK_ARG(N >= 0 && H > 0 && W > 0, "s2d: bad shape N=%d H=%d W=%d", N, H, W);
     KB_CHECK_ARG(C_in >= 1 && C_in <= S2D_MAX_CIN, "s2d: input_channels=%d unsupported (1..%d)", C_in, S2D_MAX_CIN);
