@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
 
 EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_s2d_forward', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
-           'kbnet_conv2d_forward', 'kbnet_depth_head_forward')
+           'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights')
 
 
 class KBNetConvSrc(ctypes.Structure):
@@ -38,10 +38,14 @@ def load():
     lib.kbnet_kb_workspace_bytes.restype = sz
     lib.kbnet_kb_workspace_bytes.argtypes = [i] * 9
     lib.kbnet_kb_forward.restype = i
-    lib.kbnet_kb_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp, i, f,
+    lib.kbnet_conv_wpack_bytes.restype = sz
+    lib.kbnet_conv_wpack_bytes.argtypes = [c.POINTER(i), i, i, i]
+    lib.kbnet_conv_pack_weights.restype = i
+    lib.kbnet_conv_pack_weights.argtypes = [vp, c.POINTER(i), i, i, i, vp, vp]
+    lib.kbnet_kb_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp, i, vp, vp, vp, f,
                                      vp, ll, vp, ll, vp, ll, vp, sz, vp]
     lib.kbnet_conv2d_forward.restype = i
-    lib.kbnet_conv2d_forward.argtypes = [c.POINTER(KBNetConvSrc), i, i, i, i, vp, i, i, i, i, f, vp, ll, vp]
+    lib.kbnet_conv2d_forward.argtypes = [c.POINTER(KBNetConvSrc), i, i, i, i, vp, vp, i, i, i, i, f, vp, ll, vp]
     lib.kbnet_depth_head_forward.restype = i
     lib.kbnet_depth_head_forward.argtypes = [vp, ll, c.c_double, c.c_double, vp, vp]
     _lib = lib

@@ -67,7 +67,8 @@ size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, 
 
 int kbnet_kb_forward(const float* image, long long image_stride_n, const float* depth, long long depth_stride_n,
                      const float* fused, long long fused_stride_n, const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_image, int F_i, const float* w_depth,
-                     int F_d, const float* w_proj, const float* w_fused, int F_f, float neg_slope, float* out_image,
+                     int F_d, const float* w_proj, const float* w_fused, int F_f, const void* wpack_image,
+                     const void* wpack_depth, const void* wpack_fused, float neg_slope, float* out_image,
                      long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
                      long long out_fused_stride_n, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -76,6 +77,8 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
                  "kb: null pointer argument");
     KB_CHECK_ARG((coordinates != nullptr) != (kinv != nullptr), "kb: pass exactly one of `coordinates` and `kinv`");
     KB_CHECK_ARG((fused != nullptr) == (C_f > 0), "kb: fused pointer and C_f=%d disagree", C_f);
+    KB_CHECK_ARG((wpack_image != nullptr) == (wpack_depth != nullptr) && (wpack_image != nullptr) == (wpack_fused != nullptr),
+                 "kb: pass all three packed weights or none");
     KB_CHECK_ARG(N >= 0 && C_i > 0 && C_d > 0 && H > 0 && W > 0 && F_i > 0 && F_d > 0 && F_f > 0, "kb: bad shape");
     if (N == 0) return 0;
     const long long plane = (long long)H * W;
@@ -95,7 +98,7 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
         p.n_src = 1;
         p.src[0] = make_src(image, nullptr, C_i, H, W, image_stride_n, SRC_DIRECT);
         if ((rc = finish_conv(p, N, H, W, w_image, F_i, 3, 2, 1, neg_slope, out_image, out_image_stride_n))) return rc;
-        if ((rc = conv_direct_launch(p, stream))) return rc;
+        if ((rc = conv_launch(p, wpack_image, stream))) return rc;
     }
     // conv_depth = leaky(conv3x3 s2 (cat[depth, coords]))                        net_utils.py:1351
     {
@@ -105,7 +108,7 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
         p.src[1] = coordinates ? make_src(coordinates, nullptr, 3, H, W, 3 * plane, SRC_DIRECT)
                                : make_src(kinv, nullptr, 3, H, W, 9, SRC_COORDS_KINV);
         if ((rc = finish_conv(p, N, H, W, w_depth, F_d, 3, 2, 1, neg_slope, out_depth, out_depth_stride_n))) return rc;
-        if ((rc = conv_direct_launch(p, stream))) return rc;
+        if ((rc = conv_launch(p, wpack_depth, stream))) return rc;
     }
     // z = leaky(proj_depth(depth)) at even pixels                                net_utils.py:1357
     if ((rc = kb_proj_z_launch(depth, depth_stride_n, w_proj, N, C_d, H, W, Ho, Wo, neg_slope, z, stream))) return rc;
@@ -119,13 +122,22 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
         p.src[1].zW = Wo; p.src[1].zplane = (long long)Ho * Wo;
         if (fused) p.src[2] = make_src(fused, nullptr, C_f, H, W, fused_stride_n, SRC_DIRECT);
         if ((rc = finish_conv(p, N, H, W, w_fused, F_f, 1, 2, 1, neg_slope, out_fused, out_fused_stride_n))) return rc;
-        if ((rc = conv_direct_launch(p, stream))) return rc;
+        if ((rc = conv_launch(p, wpack_fused, stream))) return rc;
     }
     return 0;
 }
 
-int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in, const float* w, int F, int ksize,
-                         int stride, int act, float neg_slope, float* out, long long out_stride_n, void* stream) {
+size_t kbnet_conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize) {
+    if (!src_channels || n_src < 1 || n_src > CONV_MAX_SRC || F <= 0) return 0;
+    return conv_wpack_bytes(src_channels, n_src, F, ksize);
+}
+
+int kbnet_conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, void* stream) {
+    return conv_pack_weights(w, src_channels, n_src, F, ksize, wpack, (cudaStream_t)stream);
+}
+
+int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in, const float* w, const void* wpack,
+                         int F, int ksize, int stride, int act, float neg_slope, float* out, long long out_stride_n, void* stream) {
     if (N == 0) return 0;
     KB_CHECK_ARG(srcs && w && out, "conv: null pointer argument");
     KB_CHECK_ARG(n_src >= 1 && n_src <= CONV_MAX_SRC, "conv: n_src=%d unsupported (1..%d)", n_src, CONV_MAX_SRC);
@@ -146,7 +158,7 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
     }
     int rc;
     if ((rc = finish_conv(p, N, H_in, W_in, w, F, ksize, stride, act, neg_slope, out, out_stride_n))) return rc;
-    return conv_direct_launch(p, (cudaStream_t)stream);
+    return conv_launch(p, wpack, (cudaStream_t)stream);
 }
 
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream) {

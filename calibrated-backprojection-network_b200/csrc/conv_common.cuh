@@ -64,6 +64,14 @@ __device__ __forceinline__ float conv_fetch(const ConvSrcDev& S, int n, int c, i
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream);
+// tensor-core engine (conv_umma.cu)
+bool conv_umma_supported(const ConvParams& p);
+int conv_umma_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
+size_t conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize);
+int conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, cudaStream_t stream);
+inline int conv_launch(const ConvParams& p, const void* wpack, cudaStream_t stream) {
+    return wpack ? conv_umma_launch(p, wpack, stream) : conv_direct_launch(p, stream);
+}
 int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int N, int C, int H, int W, int Ho, int Wo, float slope, float* z,
                      cudaStream_t stream);
 int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);

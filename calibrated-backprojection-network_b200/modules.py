@@ -125,6 +125,57 @@ def _stream(device):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# arithmetic mode of the convolutions + packed-weight cache for the tensor-core engine
+# ---------------------------------------------------------------------------------------------------------
+_PRECISION = 'bf16x3'
+
+
+def set_precision(mode):
+    """'bf16x3' (default): convolutions run on the tcgen05 tensor cores with the 3-term bf16 operand split and fp32
+    accumulation (~1e-5 relative, inside the 1e-3 parity budget).  'fp32': exact fp32 FFMA on the CUDA cores
+    (reference-grade, slow) -- the on-GPU cross-check of the tensor path."""
+    global _PRECISION
+    if mode not in ('bf16x3', 'fp32'):
+        raise ValueError('kbnet_b200: precision must be "bf16x3" or "fp32"')
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+_PACK_CACHE = {}
+
+
+def packed_weight(weight, src_channels):
+    """Device buffer with `weight` ([F, sum(src_channels), k, k]) re-laid for the tensor-core engine; None in fp32 mode.
+    Cached per (storage pointer, version counter, channel segmentation): re-packed when the parameter is updated."""
+    if _PRECISION != 'bf16x3':
+        return None
+    w = weight.detach()
+    key = (w.data_ptr(), w._version, tuple(int(c) for c in src_channels), w.device.index, tuple(w.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    lib = _lib.load()
+    wc = w.contiguous()
+    f, ctot, k, _ = wc.shape
+    assert ctot == sum(src_channels), (ctot, src_channels)
+    arr = (ctypes.c_int * len(src_channels))(*[int(c) for c in src_channels])
+    nbytes = lib.kbnet_conv_wpack_bytes(arr, len(src_channels), f, k)
+    if nbytes == 0:
+        raise RuntimeError('kbnet_b200: convolution with %d input channels / %d filters is outside the tensor-core engine' % (ctot, f))
+    buf = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = lib.kbnet_conv_pack_weights(wc.data_ptr(), arr, len(src_channels), f, k, buf.data_ptr(), _stream(w.device))
+    _lib.check(rc, 'kbnet_conv_pack_weights')
+    if len(_PACK_CACHE) > 512:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = buf
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------------------
 # SparseToDensePool
 # ---------------------------------------------------------------------------------------------------------
 class SparseToDensePool(torch.nn.Module):
@@ -264,11 +315,15 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
         wi, wd = _w(self.conv_image.weight, dev), _w(self.conv_depth.weight, dev)
         wp, wf = _w(self.proj_depth.weight, dev), _w(self.conv_fused.weight, dev)
         sn = lambda t: t.stride(0) if n > 1 else t.shape[1] * ho * wo
+        pk_i = packed_weight(wi, [c_i])
+        pk_d = packed_weight(wd, [c_d, 3])
+        pk_f = packed_weight(wf, [c_i, 3, c_f] if c_f else [c_i, 3])
+        ptr = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(dev):
             rc = lib.kbnet_kb_forward(image.data_ptr(), image_sn, depth.data_ptr(), depth_sn,
                                       fused.data_ptr() if fused is not None else None, fused_sn, coords_ptr, kinv_ptr, n, c_i, c_d, c_f, h, w,
                                       wi.data_ptr(), f_i, wd.data_ptr(), f_d, wp.data_ptr(), wf.data_ptr(), f_f,
-                                      self.negative_slope,
+                                      ptr(pk_i), ptr(pk_d), ptr(pk_f), self.negative_slope,
                                       o_i.data_ptr(), sn(o_i), o_d.data_ptr(), sn(o_d), o_f.data_ptr(), sn(o_f),
                                       ws.data_ptr(), ws_bytes, _stream(dev))
         _lib.check(rc, 'kbnet_kb_forward')

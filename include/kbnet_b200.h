@@ -79,13 +79,24 @@ int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W,
  */
 size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);
 
+/* Packed weights for the tensor-core engine (tcgen05, bf16 hi/lo operand split, fp32 accumulate).
+ * A conv whose input is the channel concatenation of `n_src` sources with `src_channels[i]` channels each gets its
+ * [F, sum(src_channels), k, k] fp32 weight re-laid once into the exact shared-memory image the kernel streams with TMA.
+ * Re-pack whenever the weight values change.  `wpack` must be 16-byte aligned device memory of kbnet_conv_wpack_bytes(). */
+size_t kbnet_conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize);
+int    kbnet_conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, void* stream);
+
+/* wpack_image / wpack_depth / wpack_fused: packed forms of w_image ({C_i}), w_depth ({C_d, 3}) and w_fused
+ * ({C_i, 3, C_f} or {C_i, 3}); pass all three to run the convolutions on the tensor cores, or all NULL for the exact-fp32
+ * CUDA-core path. */
 int kbnet_kb_forward(const float* image, long long image_stride_n,
                      const float* depth, long long depth_stride_n,
                      const float* fused, long long fused_stride_n,
                      const float* coordinates, const float* kinv,
                      int N, int C_i, int C_d, int C_f, int H, int W,
                      const float* w_image, int F_i, const float* w_depth, int F_d,
-                     const float* w_proj, const float* w_fused, int F_f, float neg_slope,
+                     const float* w_proj, const float* w_fused, int F_f,
+                     const void* wpack_image, const void* wpack_depth, const void* wpack_fused, float neg_slope,
                      float* out_image, long long out_image_stride_n,
                      float* out_depth, long long out_depth_stride_n,
                      float* out_fused, long long out_fused_stride_n,
@@ -110,7 +121,7 @@ typedef struct kbnet_conv_src {
 } kbnet_conv_src;
 
 int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in, int W_in,
-                         const float* w, int F, int ksize, int stride,
+                         const float* w, const void* wpack /* NULL = exact fp32 path */, int F, int ksize, int stride,
                          int act /* 0 none, 1 leaky */, float neg_slope,
                          float* out, long long out_stride_n, void* stream);
 

@@ -25,9 +25,17 @@ def _dims(c):
     return ci, cd, cf, c['conv_image'].shape[1], c['conv_depth'].shape[1], c['conv_fused'].shape[1]
 
 
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    kbnet_b200.set_precision('bf16x3')
+
+
 @pytest.mark.parametrize('idx', range(3))
 @pytest.mark.parametrize('path', ['coordinates', 'kinv'])
-def test_golden_cases(idx, path):
+@pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
+def test_golden_cases(idx, path, precision):
+    kbnet_b200.set_precision(precision)
     c = load_golden('kb_cases.pt')[idx]
     m = _block(*_dims(c), c['state_dict'])
     coords = c['coordinates'].to(DEV) if path == 'coordinates' else torch.inverse(c['k']).to(DEV)
