@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
 
 EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_s2d_forward', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
-           'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights')
+           'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights', 'kbnet_intrinsics_inverse')
 
 
 class KBNetConvSrc(ctypes.Structure):
@@ -46,6 +46,8 @@ def load():
                                      vp, ll, vp, ll, vp, ll, vp, sz, vp]
     lib.kbnet_conv2d_forward.restype = i
     lib.kbnet_conv2d_forward.argtypes = [c.POINTER(KBNetConvSrc), i, i, i, i, vp, vp, i, i, i, i, f, vp, ll, vp]
+    lib.kbnet_intrinsics_inverse.restype = i
+    lib.kbnet_intrinsics_inverse.argtypes = [vp, i, f, f, vp, vp, vp]
     lib.kbnet_depth_head_forward.restype = i
     lib.kbnet_depth_head_forward.argtypes = [vp, ll, c.c_double, c.c_double, vp, vp]
     _lib = lib

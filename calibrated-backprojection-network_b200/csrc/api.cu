@@ -161,6 +161,12 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
     return conv_launch(p, wpack, (cudaStream_t)stream);
 }
 
+int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y, float* kinv0, float* kinv1, void* stream) {
+    if (N == 0) return 0;
+    KB_CHECK_ARG(K && kinv0 && N > 0, "intrinsics_inverse: bad argument");
+    return intrinsics_inverse_launch(K, N, scale_x, scale_y, kinv0, kinv1, (cudaStream_t)stream);
+}
+
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream) {
     KB_CHECK_ARG(x && y && n_elem >= 0, "depth_head: bad argument");
     return depth_head_launch(x, n_elem, min_depth, max_depth, y, (cudaStream_t)stream);

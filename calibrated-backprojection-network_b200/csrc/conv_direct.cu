@@ -111,6 +111,35 @@ int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int
     return 0;
 }
 
+__device__ __forceinline__ void inv3x3(const double* a, float* out) {
+    const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    const double r = 1.0 / det;
+    out[0] = (float)(c00 * r); out[1] = (float)((a[2] * a[7] - a[1] * a[8]) * r); out[2] = (float)((a[1] * a[5] - a[2] * a[4]) * r);
+    out[3] = (float)(c01 * r); out[4] = (float)((a[0] * a[8] - a[2] * a[6]) * r); out[5] = (float)((a[2] * a[3] - a[0] * a[5]) * r);
+    out[6] = (float)(c02 * r); out[7] = (float)((a[1] * a[6] - a[0] * a[7]) * r); out[8] = (float)((a[0] * a[4] - a[1] * a[3]) * r);
+}
+
+__global__ void intrinsics_inverse_kernel(const float* __restrict__ K, int N, float sx, float sy, float* __restrict__ kinv0,
+                                          float* __restrict__ kinv1) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double a[9], b[9];
+    // element-wise scale in fp32 exactly as `k * scale` does in the reference (src/networks.py:352)
+    const float sc[9] = {sx, 1.f, sx, 1.f, sy, sy, 1.f, 1.f, 1.f};
+    for (int i = 0; i < 9; ++i) { const float k = K[n * 9 + i]; a[i] = (double)k; b[i] = (double)(k * sc[i]); }
+    inv3x3(a, kinv0 + n * 9);
+    if (kinv1) inv3x3(b, kinv1 + n * 9);
+}
+
+int intrinsics_inverse_launch(const float* K, int N, float sx, float sy, float* kinv0, float* kinv1, cudaStream_t stream) {
+    if (N == 0) return 0;
+    intrinsics_inverse_kernel<<<(N + 63) / 64, 64, 0, stream>>>(K, N, sx, sy, kinv0, kinv1);
+    KB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 __global__ void depth_head_kernel(const float* __restrict__ x, long long n, float min_d, float ratio, float* __restrict__ y) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -173,7 +173,7 @@ __device__ __forceinline__ void store_split8(uint8_t* hi_dst, uint8_t* lo_dst, c
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(a.y, b.y, c.y, d.y);
 }
 
-__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+__global__ void __launch_bounds__(UM_THREADS, 2) conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     // barrier indices
@@ -218,34 +218,77 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             const int slot = s % p.a_stages;
             mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)(s / p.a_stages)) & 1u) ^ 1u);
             uint8_t* stage = sA + (size_t)slot * a_stage_bytes;
-            for (int it = warp; it < items; it += UM_PROD_WARPS) {
-                const int blk = it % nblk;
-                const int rest = it / nblk;
-                const int py = rest % p.n_py, gi = rest / p.n_py;
-                const uint32_t g = p.groups[2 * s + gi];
-                const int nch = (g >> 8) & 0xFF, c0 = g >> 16;
-                const ConvSrcDev& S = p.src[g & 0xFF];
-                const int e = (blk << 5) + lane;
-                if (e >= p.n_entries) continue;
-                const int ei = e / p.P, ej = e - ei * p.P;
-                float v[8];
-                if (p.geo == GEO_S2K3) {
-                    const int y = 2 * (oy0 - 1 + ei) + py;
-                    const int x = 2 * (ox0 - 1 + ej);
-                    const bool yin = (y >= 0 && y < p.Hin);
+            // Loads of IPT items are issued back to back before any of them is converted: the gather is latency-bound,
+            // so the number of independent global loads in flight per thread is what sets the fill time of a stage.
+            if (p.geo == GEO_S2K3) {
+                constexpr int IPT = 2;
+                for (int base = warp; base < items; base += UM_PROD_WARPS * IPT) {
+                    float v[IPT][2][8];
+                    int ee[IPT], pyy[IPT], gii[IPT];
 #pragma unroll
-                    for (int px = 0; px < 2; ++px) {
-                        const int xx = x + px;
-                        gather8(S, n, c0, nch, y, xx, nch > 0 && yin && xx >= 0 && xx < p.Win, v);
-                        uint8_t* pl = stage + (size_t)((py * 2 + px) * 4) * p.plane_px * 16;
-                        store_split8(pl + ((size_t)gi * p.plane_px + e) * 16, pl + ((size_t)(2 + gi) * p.plane_px + e) * 16, v);
+                    for (int u = 0; u < IPT; ++u) {
+                        const int it = base + u * UM_PROD_WARPS;
+                        ee[u] = -1;
+                        if (it < items) {
+                            const int blk = it % nblk, rest = it / nblk;
+                            const int py = rest % p.n_py, gi = rest / p.n_py;
+                            const int e = (blk << 5) + lane;
+                            if (e < p.n_entries) {
+                                const uint32_t g = p.groups[2 * s + gi];
+                                const int nch = (g >> 8) & 0xFF, c0 = g >> 16;
+                                const ConvSrcDev& S = p.src[g & 0xFF];
+                                const int ei = e / p.P, ej = e - ei * p.P;
+                                const int y = 2 * (oy0 - 1 + ei) + py;
+                                const int x = 2 * (ox0 - 1 + ej);
+                                const bool yin = nch > 0 && y >= 0 && y < p.Hin;
+                                gather8(S, n, c0, nch, y, x, yin && x >= 0 && x < p.Win, v[u][0]);
+                                gather8(S, n, c0, nch, y, x + 1, yin && x + 1 >= 0 && x + 1 < p.Win, v[u][1]);
+                                ee[u] = e; pyy[u] = py; gii[u] = gi;
+                            }
+                        }
                     }
-                } else {
-                    int y, x;
-                    if (p.geo == GEO_S1) { y = oy0 - p.pad + ei; x = ox0 - p.pad + ej; }
-                    else                 { y = 2 * (oy0 + ei);   x = 2 * (ox0 + ej); }
-                    gather8(S, n, c0, nch, y, x, nch > 0 && y >= 0 && y < p.Hin && x >= 0 && x < p.Win, v);
-                    store_split8(stage + ((size_t)gi * p.plane_px + e) * 16, stage + ((size_t)(2 + gi) * p.plane_px + e) * 16, v);
+#pragma unroll
+                    for (int u = 0; u < IPT; ++u) {
+                        if (ee[u] >= 0) {
+#pragma unroll
+                            for (int px = 0; px < 2; ++px) {
+                                uint8_t* pl = stage + (size_t)((pyy[u] * 2 + px) * 4) * p.plane_px * 16;
+                                store_split8(pl + ((size_t)gii[u] * p.plane_px + ee[u]) * 16,
+                                             pl + ((size_t)(2 + gii[u]) * p.plane_px + ee[u]) * 16, v[u][px]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                constexpr int IPT = 4;
+                for (int base = warp; base < items; base += UM_PROD_WARPS * IPT) {
+                    float v[IPT][8];
+                    int ee[IPT], gii[IPT];
+#pragma unroll
+                    for (int u = 0; u < IPT; ++u) {
+                        const int it = base + u * UM_PROD_WARPS;
+                        ee[u] = -1;
+                        if (it < items) {
+                            const int blk = it % nblk, gi = it / nblk;
+                            const int e = (blk << 5) + lane;
+                            if (e < p.n_entries) {
+                                const uint32_t g = p.groups[2 * s + gi];
+                                const int nch = (g >> 8) & 0xFF, c0 = g >> 16;
+                                const ConvSrcDev& S = p.src[g & 0xFF];
+                                const int ei = e / p.P, ej = e - ei * p.P;
+                                int y, x;
+                                if (p.geo == GEO_S1) { y = oy0 - p.pad + ei; x = ox0 - p.pad + ej; }
+                                else                 { y = 2 * (oy0 + ei);   x = 2 * (ox0 + ej); }
+                                gather8(S, n, c0, nch, y, x, nch > 0 && y >= 0 && y < p.Hin && x >= 0 && x < p.Win, v[u]);
+                                ee[u] = e; gii[u] = gi;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < IPT; ++u)
+                        if (ee[u] >= 0)
+                            store_split8(stage + ((size_t)gii[u] * p.plane_px + ee[u]) * 16,
+                                         stage + ((size_t)(2 + gii[u]) * p.plane_px + ee[u]) * 16, v[u]);
                 }
             }
             fence_proxy_async_smem();
@@ -397,28 +440,35 @@ int conv_umma_launch(const ConvParams& c, const void* wpack, cudaStream_t stream
     const int w_slot_bytes = p.Npad * 64;
     const int mb_max = 512 / p.Npad;
     // ---- tile search: minimise waves * per-tile cycles under the smem / TMEM limits ------------------------------
+    // A tile that needs <= 256 TMEM columns and <= half of the shared memory lets two CTAs share an SM: one CTA's epilogue
+    // and prologue then overlap the other's MMA main loop (the kernel itself is not persistent).
+    constexpr int SMEM_HALF = 113 * 1024;
+    auto plane_px_of = [&](int R, int P, int MB) {
+        const int n_entries = (R + halo_y) * P;
+        const int max_shift = p.geo == GEO_S1 ? (taps == 9 ? 2 * P + 2 : 0) : (p.geo == GEO_S2K3 ? P + 1 : 0);
+        return roundup(n_entries > max_shift + MB * 128 ? n_entries : max_shift + MB * 128, 8);
+    };
     double best = 1e30;
     int bR = 0, bTW = 0;
     for (int parts = 1; parts <= 16; ++parts) {
         const int TW = cdiv(c.Wout, parts);
         if (parts > 1 && TW == cdiv(c.Wout, parts - 1)) continue;
         const int P = TW + halo_x;
-        for (int R = 1; R <= 64 && R <= c.Hout + 0; ++R) {
+        for (int R = 1; R <= 64 && R <= c.Hout; ++R) {
             const int MB = cdiv(R * P, 128);
             if (MB > mb_max) break;
-            const int erows = R + halo_y;
-            const int n_entries = erows * P;
-            const int max_shift = p.geo == GEO_S1 ? (taps == 9 ? 2 * P + 2 : 0) : (p.geo == GEO_S2K3 ? P + 1 : 0);
-            const int plane_px = roundup(n_entries > max_shift + MB * 128 ? n_entries : max_shift + MB * 128, 8);
-            const long long a_stage = (long long)p.n_planes * 4 * plane_px * 16;
-            if (UM_HEADER + 2 * a_stage + 2LL * w_slot_bytes > UM_SMEM_LIMIT) break;
+            const int n_entries = (R + halo_y) * P;
+            const long long a_stage = (long long)p.n_planes * 4 * plane_px_of(R, P, MB) * 16;
+            const long long smem_min = UM_HEADER + 2 * a_stage + 2LL * w_slot_bytes;
+            if (smem_min > UM_SMEM_LIMIT) break;
+            const bool co2 = MB * p.Npad <= 256 && smem_min <= SMEM_HALF;
             const long long tiles = (long long)c.N * cdiv(c.Hout, R) * cdiv(c.Wout, TW);
             const double mma = (double)p.n_stages * taps * MB * p.n_parts * 3.0 * mma_cycles(p.part_N);
             const double load = (double)p.n_stages * p.n_planes * n_entries * 64.0 / 20.0;
             const double wts = (double)p.n_stages * taps * w_slot_bytes / 40.0;
             const double epi = (double)MB * 128 * p.Npad * 4.0 / 20.0;
             double tile = mma > load ? mma : load;
-            tile = (tile > wts ? tile : wts) + epi + 4000.0;
+            tile = (tile > wts ? tile : wts) + (co2 ? 0.25 : 1.0) * (epi + 6000.0);
             const double total = (double)cdiv((int)(tiles > (1 << 30) ? (1 << 30) : tiles), 148) * tile;
             if (total < best) { best = total; bR = R; bTW = TW; }
         }
@@ -428,16 +478,14 @@ int conv_umma_launch(const ConvParams& c, const void* wpack, cudaStream_t stream
     p.MB = cdiv(p.R * p.P, 128);
     p.erows = p.R + halo_y;
     p.n_entries = p.erows * p.P;
-    {
-        const int max_shift = p.geo == GEO_S1 ? (taps == 9 ? 2 * p.P + 2 : 0) : (p.geo == GEO_S2K3 ? p.P + 1 : 0);
-        p.plane_px = roundup(p.n_entries > max_shift + p.MB * 128 ? p.n_entries : max_shift + p.MB * 128, 8);
-    }
+    p.plane_px = plane_px_of(p.R, p.P, p.MB);
     const long long a_stage = (long long)p.n_planes * 4 * p.plane_px * 16;
     p.a_stages = 2;
     p.w_slots = 2;
     long long used = UM_HEADER + p.a_stages * a_stage + (long long)p.w_slots * w_slot_bytes;
-    while (p.w_slots < UM_MAX_WSLOTS && p.w_slots < p.n_stages * taps && used + w_slot_bytes <= UM_SMEM_LIMIT) { ++p.w_slots; used += w_slot_bytes; }
-    if (p.n_stages > 2 && used + a_stage <= UM_SMEM_LIMIT) { ++p.a_stages; used += a_stage; }
+    const long long budget = (p.MB * p.Npad <= 256 && used <= SMEM_HALF) ? SMEM_HALF : UM_SMEM_LIMIT;
+    while (p.w_slots < UM_MAX_WSLOTS && p.w_slots < p.n_stages * taps && used + w_slot_bytes <= budget) { ++p.w_slots; used += w_slot_bytes; }
+    if (p.n_stages > 2 && used + a_stage <= budget) { ++p.a_stages; used += a_stage; }
     p.tmem_cols = 32;
     while (p.tmem_cols < p.MB * p.Npad) p.tmem_cols <<= 1;
     p.tiles_x = cdiv(c.Wout, p.TW);

@@ -87,9 +87,7 @@ class KBNetEncoder(torch.nn.Module):
         """K^-1 for level 0 and for levels 1..3.  The reference's scale_intrinsics closure (src/networks.py:333-352)
         always applies the level-1/level-0 ratio, whatever level it is called for; pretrained weights depend on that,
         so it is reproduced: levels 1, 2 and 3 share K * [[sx,1,sx],[1,sy,sy],[1,1,1]], sx = W1/W0, sy = H1/H0."""
-        sx, sy = w1 / w0, h1 / h0
-        scale = torch.tensor([[sx, 1.0, sx], [1.0, sy, sy], [1.0, 1.0, 1.0]], dtype=torch.float32, device=intrinsics.device)
-        return torch.inverse(intrinsics).contiguous(), torch.inverse(intrinsics * scale.view(1, 3, 3)).contiguous()
+        return ops.intrinsics_inverse(intrinsics, w1 / w0, h1 / h0)
 
     def forward(self, image, depth, intrinsics):
         slope = self.negative_slope

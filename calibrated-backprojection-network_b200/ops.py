@@ -67,3 +67,17 @@ def depth_head(x, min_predict_depth, max_predict_depth):
                                           y.data_ptr(), _stream(x.device))
     _lib.check(rc, 'kbnet_depth_head_forward')
     return y
+
+
+def intrinsics_inverse(intrinsics, scale_x=1.0, scale_y=1.0):
+    """(inverse(K), inverse(K * [[sx,1,sx],[1,sy,sy],[1,1,1]])) in one launch (reference src/networks.py:317-352)."""
+    lib = _lib.load()
+    k = intrinsics.contiguous()
+    if not k.is_cuda or k.dtype != torch.float32 or k.dim() != 3 or tuple(k.shape[1:]) != (3, 3):
+        raise RuntimeError('kbnet_b200: intrinsics must be a CUDA float32 [N,3,3] tensor')
+    k0, k1 = torch.empty_like(k), torch.empty_like(k)
+    with torch.cuda.device(k.device):
+        rc = lib.kbnet_intrinsics_inverse(k.data_ptr(), k.shape[0], float(scale_x), float(scale_y), k0.data_ptr(), k1.data_ptr(),
+                                          _stream(k.device))
+    _lib.check(rc, 'kbnet_intrinsics_inverse')
+    return k0, k1

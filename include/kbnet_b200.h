@@ -125,6 +125,11 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
                          int act /* 0 none, 1 leaky */, float neg_slope,
                          float* out, long long out_stride_n, void* stream);
 
+/* K^-1 for the KB layers -- replaces torch.inverse + the scale_intrinsics closure in KBNetEncoder.forward
+ * (src/networks.py:317-352): kinv0 = inverse(K), kinv1 = inverse(K * [[sx,1,sx],[1,sy,sy],[1,1,1]]) (may be NULL).
+ * K, kinv0, kinv1: [N,9] row-major 3x3 per sample.  One launch instead of ~12 LU / triangular-solve launches per inverse. */
+int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y, float* kinv0, float* kinv1, void* stream);
+
 /* Output head of KBNetModel.forward (src/kbnet_model.py:181-184): y = min_d / (sigmoid(x) + min_d / max_d). */
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream);
 
