@@ -144,34 +144,33 @@ def get_precision():
     return _PRECISION
 
 
-_PACK_CACHE = {}
-
-
 def packed_weight(weight, src_channels):
     """Device buffer with `weight` ([F, sum(src_channels), k, k]) re-laid for the tensor-core engine; None in fp32 mode.
-    Cached per (storage pointer, version counter, channel segmentation): re-packed when the parameter is updated."""
+    The buffer is cached ON the weight tensor object (so it dies with it -- a cache keyed on data_ptr alone would be fooled
+    by the allocator handing a freed weight's address to another layer) and is re-packed when the version counter or the
+    storage changes (in-place updates, load_state_dict, .to())."""
     if _PRECISION != 'bf16x3':
         return None
-    w = weight.detach()
-    key = (w.data_ptr(), w._version, tuple(int(c) for c in src_channels), w.device.index, tuple(w.shape))
-    hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    key = (weight.data_ptr(), weight._version, tuple(int(c) for c in src_channels), tuple(weight.shape))
+    cache = weight.__dict__.get('_kbnet_pack') if hasattr(weight, '__dict__') else None
+    if cache is not None and cache[0] == key:
+        return cache[1]
     lib = _lib.load()
-    wc = w.contiguous()
+    wc = weight.detach().contiguous()
     f, ctot, k, _ = wc.shape
     assert ctot == sum(src_channels), (ctot, src_channels)
     arr = (ctypes.c_int * len(src_channels))(*[int(c) for c in src_channels])
     nbytes = lib.kbnet_conv_wpack_bytes(arr, len(src_channels), f, k)
     if nbytes == 0:
         raise RuntimeError('kbnet_b200: convolution with %d input channels / %d filters is outside the tensor-core engine' % (ctot, f))
-    buf = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
-    with torch.cuda.device(w.device):
-        rc = lib.kbnet_conv_pack_weights(wc.data_ptr(), arr, len(src_channels), f, k, buf.data_ptr(), _stream(w.device))
+    buf = torch.empty((nbytes,), dtype=torch.uint8, device=wc.device)
+    with torch.cuda.device(wc.device):
+        rc = lib.kbnet_conv_pack_weights(wc.data_ptr(), arr, len(src_channels), f, k, buf.data_ptr(), _stream(wc.device))
     _lib.check(rc, 'kbnet_conv_pack_weights')
-    if len(_PACK_CACHE) > 512:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = buf
+    try:
+        weight.__dict__['_kbnet_pack'] = (key, buf)
+    except Exception:
+        pass
     return buf
 
 
@@ -315,9 +314,9 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
         wi, wd = _w(self.conv_image.weight, dev), _w(self.conv_depth.weight, dev)
         wp, wf = _w(self.proj_depth.weight, dev), _w(self.conv_fused.weight, dev)
         sn = lambda t: t.stride(0) if n > 1 else t.shape[1] * ho * wo
-        pk_i = packed_weight(wi, [c_i])
-        pk_d = packed_weight(wd, [c_d, 3])
-        pk_f = packed_weight(wf, [c_i, 3, c_f] if c_f else [c_i, 3])
+        pk_i = packed_weight(self.conv_image.weight, [c_i])
+        pk_d = packed_weight(self.conv_depth.weight, [c_d, 3])
+        pk_f = packed_weight(self.conv_fused.weight, [c_i, 3, c_f] if c_f else [c_i, 3])
         ptr = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(dev):
             rc = lib.kbnet_kb_forward(image.data_ptr(), image_sn, depth.data_ptr(), depth_sn,

@@ -47,7 +47,7 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None):
     for i, (t, sn, mode) in enumerate(parsed):
         arr[i].ptr, arr[i].C, arr[i].H, arr[i].W, arr[i].stride_n, arr[i].mode = t.data_ptr(), t.shape[1], t.shape[2], t.shape[3], sn, mode
     osn = out.stride(0) if n > 1 else f * ho * wo
-    pk = packed_weight(w, [t.shape[1] for t, _, _ in parsed])
+    pk = packed_weight(weight, [t.shape[1] for t, _, _ in parsed])
     with torch.cuda.device(dev):
         rc = lib.kbnet_conv2d_forward(arr, len(parsed), n, h_in, w_in, w.data_ptr(), pk.data_ptr() if pk is not None else None,
                                       f, k, stride,
