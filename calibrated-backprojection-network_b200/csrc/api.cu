@@ -53,10 +53,25 @@ const char* kbnet_last_error(void) { return g_err; }
 unsigned long long kbnet_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
-                      int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
-                      float* out, float* pyramid, void* stream) {
-    return s2d_forward(x, N, C_in, H, W, min_sizes, n_min, max_sizes, n_max, w_1x1, n_conv, n_filter, w_3x3, neg_slope, out,
-                       pyramid, (cudaStream_t)stream);
+                      int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack,
+                      float neg_slope, float* out, float* pyramid, void* stream) {
+    KB_CHECK_ARG((n_min == 0 || min_sizes) && (n_max == 0 || max_sizes), "s2d: null pool size list");
+    static const int none[1] = {0};
+    return s2d_forward(x, N, C_in, H, W, min_sizes ? min_sizes : none, n_min, max_sizes ? max_sizes : none, n_max, w_1x1, n_conv,
+                       n_filter, w_3x3, wpack, neg_slope, out, pyramid, (cudaStream_t)stream);
+}
+
+size_t kbnet_s2d_wpack_bytes(int C_in, const int* min_sizes, int n_min, const int* max_sizes, int n_max, int n_conv, int n_filter,
+                             float neg_slope) {
+    static const int none[1] = {0};
+    return s2d_wpack_bytes(C_in, min_sizes ? min_sizes : none, n_min, max_sizes ? max_sizes : none, n_max, n_conv, n_filter, neg_slope);
+}
+
+int kbnet_s2d_pack_weights(const float* const* w_1x1, int n_conv, const float* w_3x3, int C_in, const int* min_sizes, int n_min,
+                           const int* max_sizes, int n_max, void* wpack, void* stream) {
+    static const int none[1] = {0};
+    return s2d_pack_weights(w_1x1, n_conv, w_3x3, C_in, min_sizes ? min_sizes : none, n_min, max_sizes ? max_sizes : none, n_max, wpack,
+                            (cudaStream_t)stream);
 }
 
 size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f) {

@@ -77,7 +77,10 @@ int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int
 int intrinsics_inverse_launch(const float* K, int N, float sx, float sy, float* kinv0, float* kinv1, cudaStream_t stream);
 int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);
 int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
-                int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
+                int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack, float neg_slope,
                 float* out, float* pyramid, cudaStream_t stream);
+size_t s2d_wpack_bytes(int C_in, const int* min_sizes, int n_min, const int* max_sizes, int n_max, int n_conv, int n_filter, float slope);
+int s2d_pack_weights(const float* const* w_1x1, int n_conv, const float* w_3x3, int C_in, const int* min_sizes, int n_min,
+                     const int* max_sizes, int n_max, void* wpack, cudaStream_t stream);
 
 }  // namespace kbnet

@@ -1,63 +1,326 @@
-// Fused SparseToDensePool forward for sm_100a.
+// Fused SparseToDensePool forward for sm_100a -- ONE kernel for reference src/networks.py:2168-2196.
 //
-// Replaces reference src/networks.py:2168-2196 (~35 ATen launches, every intermediate plane through HBM)
-// with ONE kernel: per output tile the sparse-depth halo tile is staged in shared memory once, all min/max
-// pool radii are produced by a separable nested-window sweep held in registers, the 1x1 fusion chain runs
-// in registers, and the 3x3 conv reads its 10-channel input from shared memory.  HBM traffic = read x once
-// (+halo from L2), write out once.
+// Per CTA: a 12 x 64 output tile of one sample, 256 threads, ~80 KB of shared memory (2 CTAs per SM).
 //
-// Tile geometry (template): TH x TW output pixels per CTA.
-//   pyramid region : rows [y0-1, y0+TH+1)  cols [x0-4, x0+TW+4)      (PH x PW, 3x3-conv halo, 4-aligned in x)
-//   z tile         : pyramid region grown by R (max pool radius) on every side (ZH x ZW)
-// Pool semantics (bit-exact vs ATen, see oracle/pools_np.py): empty <=> z == 0; min over non-empty values with
-// 999 as the "empty" flag and a result of exactly 999 mapped to 0; max with -inf padding; NaN propagates.
-#include "common.cuh"
+//   A. TMA      the sparse-depth halo tile and the second raw channel are staged into shared memory by
+//               cp.async.bulk.tensor (3-D tiled tensor map over [N*C, H, W], out-of-image elements zero-filled), the
+//               pre-packed weights by one cp.async.bulk, all completing on one mbarrier.
+//   B. pass 1   vertical nested-window sweep: one thread per tile column and 5-row segment produces, for every pool
+//               radius, the column min / max (FMNMX3.NAN: one instruction per radius step) -> V planes in smem.
+//               The raw x channels are split to bf16 hi/lo for the 3x3 conv in the same phase.
+//   C. pass 2   horizontal sweep on 4-pixel strips, all in registers: pool pyramid -> 999->0 fix -> the 1x1 fusion chain
+//               (exact fp32, packed FFMA2 on pixel pairs, weights broadcast from smem) -> LeakyReLU -> Q (8 channels),
+//               written to smem as bf16 hi/lo "chunk planes" (16 bytes = 8 channels of one pixel).
+//   D. 3x3 conv on the legacy tensor path (mma.sync m16n8k16 bf16, fp32 accumulate) with the 3-term operand split
+//               a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (16 mantissa bits per operand, ~1e-5 relative).  N = 8 filters is
+//               exactly one n8 tile; K = 9 taps x 8 Q channels + 3 rows x (3 dx x C_in) raw channels = 96 = 6 k16 steps.
+//               A fragments come from the chunk planes with ldmatrix (a tap is a row-address shift, no im2col) and are
+//               reused for the three output rows a Q row contributes to; the B fragments live in registers.
+//               Epilogue: LeakyReLU -> NCHW stores (each store instruction writes four full 32-byte sectors).
+//
+// Why not tcgen05 here: with N = 8 a tcgen05.mma is bounded by streaming its 128 x 16 A tile from shared memory
+// (>= 47 clk per 128 pixels per k16 step measured, profiles/r01_umma_probe.md) -- 3x slower than mma.sync for this shape
+// (2.13 clk per m16n8k16 per SM measured, profiles/r01_pipe_probe.log).  The dense KB convolutions do use tcgen05.
+//
+// Pool semantics (bit-exact vs ATen, oracle/pools_np.py): empty <=> z == 0; min over non-empty values with 999 as the
+// "empty" flag and a result of exactly 999 mapped to 0; out-of-image pixels ignored (+inf / -inf); NaN propagates.
+// Inside the kernel the pool planes are kept in canonical order (min pools by ascending radius, then max pools by
+// ascending radius); the first 1x1 weight matrix is permuted accordingly when it is packed.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_common.cuh"
+#include "umma.cuh"
 
 namespace kbnet {
 
-constexpr int S2D_NF = 8;          // n_filter supported by the register-resident 1x1 chain
-constexpr int S2D_MAX_POOL = 16;
-constexpr int S2D_MAX_CONV = 8;
-constexpr int S2D_MAX_CIN = 8;
+int s2d_generic_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
+                        int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
+                        float* out, float* pyramid, cudaStream_t stream);
 
-struct S2DParams {
+namespace {
+
+using namespace ptx;
+typedef unsigned long long u64;
+
+constexpr int NF = 8;            // n_filter of the fast path
+constexpr int TH = 12, TW = 64;  // output tile
+constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+12  (14 x 17 = 238 strips: one round of 256 threads)
+constexpr int LV = 5;            // pass-1 rows per work item
+constexpr int PHV = 15;          // rows of the V planes = 3 * LV (one more than PH)
+constexpr int PW = TW + 4;       // conv-input cols   x0-2 .. x0+65  (17 strips of 4)
+constexpr int XP = PW + 4;       // smem pitch of the raw-channel tile: TMA boxes start at x0-4 (16-byte aligned coordinate)
+constexpr int NT = 256;
+constexpr int LH = 4;            // pass-2 strip width
+constexpr int MAX_POOL = 16;
+constexpr int MAX_CONV = 8;
+constexpr int SMEM_2CTA = 113 * 1024;
+constexpr int WB_BYTES = 6 * 2 * 32 * 8;
+static_assert(PHV % LV == 0 && PHV >= PH && PW % LH == 0 && TH % 2 == 0, "tiling");
+
+struct PoolSpec {            // canonical plane order: min pools by ascending radius, then max pools by ascending radius
+    int n_pool, n_min;
+    int radius[MAX_POOL];    // radius of canonical plane k
+    int chan[MAX_POOL];      // pyramid channel (reference order) of canonical plane k
+    unsigned min_mask, max_mask;  // bit r set <=> a min / max pool of radius r exists
+    int rmax_min, rmax_max;
+};
+
+struct WeightSrc {  // raw weight tensors + the canonical plane -> pyramid channel map
+    const float* w1x1[MAX_CONV];
+    const float* w3x3;
+    int n_conv, n_pool, C_in;
+    int chan[MAX_POOL];
+};
+
+struct FastParams {
     const float* x;
     float* out;
     float* pyramid;
     int N, C_in, H, W;
-    int n_pool, n_min;
-    int radius[S2D_MAX_POOL];
-    unsigned min_mask, max_mask;  // bit r set <=> some min / max pool has radius r
-    int rmax_min, rmax_max;
-    const float* w1x1[S2D_MAX_CONV];
+    PoolSpec ps;
+    WeightSrc ws;
     int n_conv;
-    const float* w3x3;
+    const uint8_t* wpack;  // pre-packed smem image of the weights (s2d_pack_weights), or nullptr: stage from the raw tensors
     float slope;
     int tiles_x, tiles_y;
+    int use_tma;
 };
 
-template <int TH, int TW, int R, int LV, int LH, int NT>
-__global__ void __launch_bounds__(NT) s2d_fused_kernel(const S2DParams p) {
-    constexpr int PH = TH + 2;
-    constexpr int PW = TW + 8;
-    constexpr int ZH = PH + 2 * R;
-    constexpr int ZW = PW + 2 * R;
-    constexpr int NF = S2D_NF;
-    static_assert(PH % LV == 0, "vertical strips must tile the pyramid rows");
-    static_assert(PW % LH == 0 && LH % 4 == 0, "horizontal strips are float4 multiples");
-    static_assert(R % 4 == 0 && TW % 4 == 0, "alignment");
+__host__ __device__ inline int w1d_bytes(int n_pool, int n_conv) { return (((NF * n_pool + (n_conv - 1) * NF * NF) * 8) + 15) & ~15; }
 
-    extern __shared__ __align__(16) float smem[];
-    const int n_cin_tot = NF + p.C_in;
-    // layout: [w1x1 | w3x3 | V planes | z tiles (fmin,fmax)  -- later aliased by the conv input planes]
-    const int n_w1 = NF * p.n_pool + (p.n_conv - 1) * NF * NF;
-    const int n_w3 = n_cin_tot * 9 * NF;
-    float* s_w1 = smem;
-    float* s_w3 = s_w1 + ((n_w1 + 3) & ~3);
-    float* s_V = s_w3 + ((n_w3 + 3) & ~3);
-    float* s_zmin = s_V + p.n_pool * PH * ZW;
-    float* s_zmax = s_zmin + ZH * ZW;
-    float* s_cin = s_zmin;  // conv input planes [NF + C_in][PH][PW] alias the (dead) z tiles
+struct Layout {  // byte offsets into dynamic shared memory (same function on host and device)
+    int w1d, wB, xc, v, z, x1, qhi, qlo, total;
+};
+__host__ __device__ inline Layout make_layout(int R, int n_pool, int n_conv) {
+    const int ZW = PW + 2 * R, ZH = PHV + 2 * R, ZP = ZW + 4;
+    Layout L;
+    int o = 16;  // [0,8): mbarrier
+    L.w1d = o; o += w1d_bytes(n_pool, n_conv);
+    L.wB = o; o += WB_BYTES;
+    L.xc = o; o += PH * PW * 8;
+    o = (o + 15) & ~15;
+    L.v = o; o += n_pool * PHV * ZW * 4;
+    o = (o + 127) & ~127;
+    L.z = o;                                       // union: {z tile, x1 tile} (dead after phase B)  /  {Q hi, Q lo}
+    L.x1 = (L.z + ZH * ZP * 4 + 127) & ~127;
+    const int end_in = L.x1 + PH * XP * 4;
+    L.qhi = o;
+    L.qlo = L.qhi + PH * PW * 16;
+    const int end_q = L.qlo + PH * PW * 16;
+    L.total = end_in > end_q ? end_in : end_q;
+    return L;
+}
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// LeakyReLU for 0 <= slope <= 1:  max(v, slope * v)  (NaN stays NaN: both operands are NaN)
+__device__ __forceinline__ float leaky01(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ u64 leaky01x2(u64 v, u64 slope2) {
+    float a, b, sa, sb;
+    unpack2(v, a, b);
+    unpack2(fmul2(v, slope2), sa, sb);
+    return pack2(fmaxf(a, sa), fmaxf(b, sb));
+}
+// two fp32 -> packed bf16 (a in the low half), round to nearest
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// (a, b) -> hi pair by truncation (one PRMT), lo pair = rn(residual); 16 mantissa bits in total
+__device__ __forceinline__ void split_trunc(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    hi = __byte_perm(ua, ub, 0x7632);
+    lo = cvt_bf16x2(a - __uint_as_float(ua & 0xFFFF0000u), b - __uint_as_float(ub & 0xFFFF0000u));
+}
+// same with a rounded hi part (safe for arbitrary NaN payloads of raw inputs)
+__device__ __forceinline__ void split_rn(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = cvt_bf16x2(a, b);
+    lo = cvt_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void hmma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// The innermost coordinate of a tiled TMA load must be a multiple of 16 bytes (checked on hardware, tools/tma_probe.cu:
+// an unaligned coordinate raises "illegal instruction"); negative / out-of-range coordinates are fine and read as zero.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
+// ---- weight image: [w1d : 1x1 weights duplicated (w, w), layer 0 as [canonical plane][j], layers >= 1 as [k][j]]
+//                    [wB  : 3x3 weights as per-lane mma B fragments [kstep = dy*2 + half][hi|lo][lane] -> (b0, b1)]
+//   half 0: k 0-7 = Q channels at dx 0, k 8-15 = Q channels at dx 1;  half 1: k 0-7 = Q at dx 2, k 8-15 = raw x slots
+//   (slot s = c + C_in * dx, s < 3 * C_in).  B fragment: n = lane / 4, b0 holds k = 2t, 2t+1, b1 holds k = 2t+8, 2t+9.
+__device__ __forceinline__ void build_weight_image(const WeightSrc& ws, uint8_t* dst, int tid, int nthreads) {
+    float2* w1d = reinterpret_cast<float2*>(dst);
+    const int np = ws.n_pool;
+    for (int i = tid; i < NF * np; i += nthreads) {
+        const int k = i / NF, j = i - k * NF;
+        const float w = __ldg(ws.w1x1[0] + j * np + ws.chan[k]);
+        w1d[i] = make_float2(w, w);
+    }
+    for (int l = 1; l < ws.n_conv; ++l)
+        for (int i = tid; i < NF * NF; i += nthreads) {
+            const int k = i >> 3, j = i & 7;
+            const float w = __ldg(ws.w1x1[l] + j * NF + k);
+            w1d[NF * np + (l - 1) * NF * NF + i] = make_float2(w, w);
+        }
+    uint32_t* wB = reinterpret_cast<uint32_t*>(dst + w1d_bytes(np, ws.n_conv));
+    const int ctot = NF + ws.C_in;
+    for (int i = tid; i < 6 * 32 * 2; i += nthreads) {
+        const int reg = i & 1, lane = (i >> 1) & 31, ks = i >> 6;
+        const int nn = lane >> 2, t = lane & 3;
+        const int dy = ks >> 1, half = ks & 1;
+        float w[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int slot = 2 * t + e;  // within the 8-slot chunk; reg selects the chunk
+            int c = -1, dx = 0;
+            if (reg == 0 || half == 0) {  // a Q chunk
+                c = slot;
+                dx = half == 0 ? reg : 2;
+            } else if (slot < 3 * ws.C_in) {
+                c = NF + slot % ws.C_in;
+                dx = slot / ws.C_in;
+            }
+            w[e] = c >= 0 ? __ldg(ws.w3x3 + (((size_t)nn * ctot + c) * 3 + dy) * 3 + dx) : 0.f;
+        }
+        uint32_t hi, lo;
+        split_rn(w[0], w[1], hi, lo);
+        wB[((ks * 2 + 0) * 32 + lane) * 2 + reg] = hi;
+        wB[((ks * 2 + 1) * 32 + lane) * 2 + reg] = lo;
+    }
+}
+
+__global__ void s2d_pack_weights_kernel(const WeightSrc ws, uint8_t* dst) { build_weight_image(ws, dst, threadIdx.x, blockDim.x); }
+
+// ---- pass 1: vertical nested-window sweep of one tile column segment -----------------------------------------------
+template <int R, bool BORDER>
+__device__ __forceinline__ void pass1(const FastParams& p, const float* s_z, float* s_V, int tid, int gy0, int gx0) {
+    constexpr int ZW = PW + 2 * R, ZP = ZW + 4;
+    constexpr int NV = LV + 2 * R;
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned min_mask = p.ps.min_mask, max_mask = p.ps.max_mask;
+    const int n_min = p.ps.n_min;
+    for (int it = tid; it < ZW * (PHV / LV); it += NT) {
+        const int seg = it / ZW, j = it - seg * ZW;
+        const int rbase = seg * LV;
+        float f[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) f[i] = s_z[(rbase + i) * ZP + j + 2];
+        bool colin = true;
+        if (BORDER) colin = (unsigned)(gx0 + j) < (unsigned)p.W;
+        float* vdst = s_V + rbase * ZW + j;
+        if (min_mask) {
+            float g[NV], m[LV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                g[i] = (f[i] == 0.f) ? 999.f : f[i];
+                if (BORDER) g[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? g[i] : INF;
+            }
+#pragma unroll
+            for (int i = 0; i < LV; ++i) m[i] = g[R + i];
+#pragma unroll
+            for (int r = 1; r <= R; ++r) {
+                if ((min_mask >> r) != 0u) {  // some min pool has radius >= r
+#pragma unroll
+                    for (int i = 0; i < LV; ++i) m[i] = min_nan(m[i], min_nan(g[R + i - r], g[R + i + r]));
+                    if ((min_mask >> r) & 1u) {
+                        float* dst = vdst + __popc(min_mask & ((1u << r) - 1u)) * (PHV * ZW);
+#pragma unroll
+                        for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
+                    }
+                }
+            }
+        }
+        if (max_mask) {
+            float m[LV];
+            if (BORDER) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) f[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? f[i] : -INF;
+            }
+#pragma unroll
+            for (int i = 0; i < LV; ++i) m[i] = f[R + i];
+#pragma unroll
+            for (int r = 1; r <= R; ++r) {
+                if ((max_mask >> r) != 0u) {
+#pragma unroll
+                    for (int i = 0; i < LV; ++i) m[i] = max_nan(m[i], max_nan(f[R + i - r], f[R + i + r]));
+                    if ((max_mask >> r) & 1u) {
+                        float* dst = vdst + (n_min + __popc(max_mask & ((1u << r) - 1u))) * (PHV * ZW);
+#pragma unroll
+                        for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// horizontal window of radius rk around the 4 strip pixels (v[R + i] is pixel i): min / max are order-independent, so the
+// radius steps run from rk down to 1 through a fall-through switch (no predicated-off work for small radii)
+template <int R, bool IS_MIN>
+__device__ __forceinline__ void hwindow(const float (&v)[LH + 2 * R], int rk, float (&m)[LH]) {
+#pragma unroll
+    for (int i = 0; i < LH; ++i) m[i] = v[R + i];
+#define KB_STEP(r)                                                                                            \
+    case r:                                                                                                   \
+        if (r <= R) {                                                                                         \
+            _Pragma("unroll") for (int i = 0; i < LH; ++i) {                                                  \
+                const float a = v[(R + i - r) >= 0 ? (R + i - r) : 0], b = v[(R + i + r) < LH + 2 * R ? (R + i + r) : 0]; \
+                m[i] = IS_MIN ? min_nan(m[i], min_nan(a, b)) : max_nan(m[i], max_nan(a, b));                  \
+            }                                                                                                 \
+        }
+    switch (rk) {
+        KB_STEP(16) KB_STEP(15) KB_STEP(14) KB_STEP(13) KB_STEP(12) KB_STEP(11) KB_STEP(10) KB_STEP(9)
+        KB_STEP(8) KB_STEP(7) KB_STEP(6) KB_STEP(5) KB_STEP(4) KB_STEP(3) KB_STEP(2) KB_STEP(1)
+        default: break;
+    }
+#undef KB_STEP
+}
+
+template <int R>
+__global__ void __launch_bounds__(NT, 2)
+s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_x1) {
+    constexpr int ZW = PW + 2 * R, ZH = PHV + 2 * R, ZP = ZW + 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int np = p.ps.n_pool;
+    const Layout L = make_layout(R, np, p.n_conv);
+    float* s_w1d = reinterpret_cast<float*>(smem + L.w1d);
+    uint2* s_wB = reinterpret_cast<uint2*>(smem + L.wB);
+    uint2* s_xc = reinterpret_cast<uint2*>(smem + L.xc);
+    float* s_V = reinterpret_cast<float*>(smem + L.v);
+    float* s_z = reinterpret_cast<float*>(smem + L.z);
+    float* s_x1 = reinterpret_cast<float*>(smem + L.x1);
+    uint4* s_qhi = reinterpret_cast<uint4*>(smem + L.qhi);
+    uint4* s_qlo = reinterpret_cast<uint4*>(smem + L.qlo);
+    const uint32_t bar = smem_u32(smem);
 
     const int tid = threadIdx.x;
     int b = blockIdx.x;
@@ -68,325 +331,382 @@ __global__ void __launch_bounds__(NT) s2d_fused_kernel(const S2DParams p) {
     const int x0 = tx * TW, y0 = ty * TH;
     const int H = p.H, W = p.W;
     const size_t plane = (size_t)H * W;
-    const float* xin = p.x + (size_t)n * p.C_in * plane;
+    const int gy0 = y0 - 1 - R, gx0 = x0 - 2 - R;  // image coordinates of logical z-tile element (0, 0) (smem column 2)
+    const int C_in = p.C_in;
+    const float slope = p.slope;
 
-    // ---- stage weights -------------------------------------------------------------------------
-    for (int i = tid; i < NF * p.n_pool; i += NT) s_w1[i] = __ldg(p.w1x1[0] + i);
-    for (int l = 1; l < p.n_conv; ++l)
-        for (int i = tid; i < NF * NF; i += NT) s_w1[NF * p.n_pool + (l - 1) * NF * NF + i] = __ldg(p.w1x1[l] + i);
-    // w3x3 [j][c][dy][dx] -> smem [c][dy][dx][j] so the 8 output filters of one tap are one 32-byte row
-    for (int i = tid; i < n_w3; i += NT) {
-        const int j = i / (n_cin_tot * 9), rem = i % (n_cin_tot * 9);
-        s_w3[rem * NF + j] = __ldg(p.w3x3 + i);
+    // ---- A. stage the input tile and the weights ---------------------------------------------------------------------
+    const bool bulk_w = p.wpack != nullptr;
+    const uint32_t wbytes = (uint32_t)(w1d_bytes(np, p.n_conv) + WB_BYTES);
+    if (tid == 0 && (p.use_tma || bulk_w)) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+        uint32_t bytes = bulk_w ? wbytes : 0u;
+        if (p.use_tma) bytes += ZH * ZP * 4 + (C_in > 1 ? PH * XP * 4 : 0);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (p.use_tma) {
+            tma_load_3d(smem_u32(s_z), &tm_z, gx0 - 2, gy0, n * C_in, bar);
+            if (C_in > 1) tma_load_3d(smem_u32(s_x1), &tm_x1, x0 - 4, y0 - 1, n * C_in + 1, bar);
+        }
+        if (bulk_w) bulk_g2s(smem_u32(s_w1d), p.wpack, wbytes, bar);
     }
-
-    // ---- 1. stage the z halo tile, already transformed for the two chains -----------------------
-    {
-        const int gy0 = y0 - 1 - R, gx0 = x0 - 4 - R;
-        for (int idx = tid; idx < ZH * ZW; idx += NT) {
-            const int i = idx / ZW, j = idx - i * ZW;
-            const int gy = gy0 + i, gx = gx0 + j;
-            float fmn = __int_as_float(0x7f800000), fmx = __int_as_float(0xff800000);
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                const float z = __ldg(xin + (size_t)gy * W + gx);
-                fmn = (z == 0.f) ? 999.f : z;
-                fmx = z;
+    if (!p.use_tma) {  // shapes the tensor map cannot describe (W % 4 != 0, unaligned base): plain loads, same smem image
+        const float* xin = p.x + (size_t)n * C_in * plane;
+        for (int idx = tid; idx < ZH * ZP; idx += NT) {
+            const int i = idx / ZP, j = idx - i * ZP;
+            const int gy = gy0 + i, gx = gx0 - 2 + j;
+            s_z[idx] = ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) ? __ldg(xin + (size_t)gy * W + gx) : 0.f;
+        }
+        if (C_in > 1)
+            for (int idx = tid; idx < PH * XP; idx += NT) {
+                const int i = idx / XP, j = idx - i * XP;
+                const int gy = y0 - 1 + i, gx = x0 - 4 + j;
+                s_x1[idx] = ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) ? __ldg(xin + plane + (size_t)gy * W + gx) : 0.f;
             }
-            s_zmin[idx] = fmn;
-            s_zmax[idx] = fmx;
+    }
+    if (!bulk_w) build_weight_image(p.ws, smem + L.w1d, tid, NT);
+    __syncthreads();
+    if (p.use_tma || bulk_w) mbar_wait(bar, 0);
+
+    // ---- B. pass 1 (vertical) + raw-channel split -------------------------------------------------------------------
+    {
+        const bool border = gy0 < 0 || gx0 < 0 || gy0 + ZH > H || gx0 + ZW > W;
+        if (border) pass1<R, true>(p, s_z, s_V, tid, gy0, gx0);
+        else        pass1<R, false>(p, s_z, s_V, tid, gy0, gx0);
+        // raw channels of the 3x3 conv input as packed bf16: .x = hi pair, .y = lo pair.
+        //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
+        for (int idx = tid; idx < PH * PW; idx += NT) {
+            const int pr = idx / PW, c = idx - pr * PW;
+            const float a = s_z[(pr + R) * ZP + c + R + 2];
+            const float bb = C_in > 1 ? s_x1[pr * XP + c + 2] : s_z[(pr + R) * ZP + c + R + 3];
+            uint32_t hi, lo;
+            split_rn(a, bb, hi, lo);
+            s_xc[idx] = make_uint2(hi, lo);
         }
     }
     __syncthreads();
 
-    // ---- 2. vertical nested-window sweep: V[k][row][col] = min/max over rows [row-r_k, row+r_k] ---
+    // ---- C. pass 2 (horizontal) -> pyramid -> 1x1 chain -> Q chunk planes ----------------------------------------------
     {
-        constexpr int NSV = PH / LV;
-        for (int s = tid; s < ZW * NSV; s += NT) {
-            const int cx = s % ZW, js = s / ZW;
-            const int rbase = js * LV;
-            if (p.n_min > 0) {
-                float f[LV + 2 * R], m[LV];
+        constexpr int NS = PW / LH;
+        const u64 slope2 = pack2(slope, slope);
+        const int n_min = p.ps.n_min;
+        for (int s = tid; s < PH * NS; s += NT) {
+            const int pr = s / NS, c0 = (s - pr * NS) * LH;
+            const int gy = y0 - 1 + pr, gxb = x0 - 2 + c0;
+            const bool want_pyr = p.pyramid != nullptr && pr >= 1 && pr <= TH && gy < H;
+            u64 acc[NF][2];
 #pragma unroll
-                for (int i = 0; i < LV + 2 * R; ++i) f[i] = s_zmin[(rbase + i) * ZW + cx];
-#pragma unroll
-                for (int i = 0; i < LV; ++i) m[i] = f[R + i];
-#pragma unroll
-                for (int r = 1; r <= R; ++r) {
-                    if (r <= p.rmax_min) {
-#pragma unroll
-                        for (int i = 0; i < LV; ++i) m[i] = min_nan(m[i], min_nan(f[R + i - r], f[R + i + r]));
-                        if ((p.min_mask >> r) & 1u) {
-                            for (int k = 0; k < p.n_min; ++k)
-                                if (p.radius[k] == r) {
-                                    float* dst = s_V + (k * PH + rbase) * ZW + cx;
-#pragma unroll
-                                    for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
-                                }
-                        }
-                    }
-                }
-            }
-            if (p.n_pool > p.n_min) {
-                float f[LV + 2 * R], m[LV];
-#pragma unroll
-                for (int i = 0; i < LV + 2 * R; ++i) f[i] = s_zmax[(rbase + i) * ZW + cx];
-#pragma unroll
-                for (int i = 0; i < LV; ++i) m[i] = f[R + i];
-#pragma unroll
-                for (int r = 1; r <= R; ++r) {
-                    if (r <= p.rmax_max) {
-#pragma unroll
-                        for (int i = 0; i < LV; ++i) m[i] = max_nan(m[i], max_nan(f[R + i - r], f[R + i + r]));
-                        if ((p.max_mask >> r) & 1u) {
-                            for (int k = p.n_min; k < p.n_pool; ++k)
-                                if (p.radius[k] == r) {
-                                    float* dst = s_V + (k * PH + rbase) * ZW + cx;
-#pragma unroll
-                                    for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
-                                }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- 3. horizontal sweep -> pyramid values in registers -> 1x1 fusion chain -> conv input planes
-    {
-        constexpr int NSH = PW / LH;
-        const float slope = p.slope;
-        for (int s = tid; s < PH * NSH; s += NT) {
-            const int pr = s / NSH, hs = s - pr * NSH;
-            const int c0 = hs * LH;
-            const int gy = y0 - 1 + pr, gxb = x0 - 4 + c0;
-            const bool row_in = (gy >= 0 && gy < H);
-            const bool core_row = (pr >= 1 && pr <= TH);
-            float acc[NF][LH];
-#pragma unroll
-            for (int j = 0; j < NF; ++j)
-#pragma unroll
-                for (int i = 0; i < LH; ++i) acc[j][i] = 0.f;
-
-            for (int k = 0; k < p.n_pool; ++k) {
-                const float* src = s_V + (k * PH + pr) * ZW + c0;
+            for (int j = 0; j < NF; ++j) acc[j][0] = acc[j][1] = 0ull;
+            for (int k = 0; k < np; ++k) {
+                const float* src = s_V + (k * PHV + pr) * ZW + c0;
                 float v[LH + 2 * R], m[LH];
+                const int rk = p.ps.radius[k];
 #pragma unroll
                 for (int q = 0; q < (LH + 2 * R) / 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
-#pragma unroll
-                for (int i = 0; i < LH; ++i) m[i] = v[R + i];
-                const int rk = p.radius[k];
-                if (k < p.n_min) {
-#pragma unroll
-                    for (int r = 1; r <= R; ++r)
-                        if (r <= rk) {
-#pragma unroll
-                            for (int i = 0; i < LH; ++i) m[i] = min_nan(m[i], min_nan(v[R + i - r], v[R + i + r]));
-                        }
+                if (k < n_min) {
+                    hwindow<R, true>(v, rk, m);
 #pragma unroll
                     for (int i = 0; i < LH; ++i) m[i] = (m[i] == 999.f) ? 0.f : m[i];
                 } else {
-#pragma unroll
-                    for (int r = 1; r <= R; ++r)
-                        if (r <= rk) {
-#pragma unroll
-                            for (int i = 0; i < LH; ++i) m[i] = max_nan(m[i], max_nan(v[R + i - r], v[R + i + r]));
-                        }
+                    hwindow<R, false>(v, rk, m);
                 }
-                if (p.pyramid != nullptr && row_in && core_row) {
-                    float* dst = p.pyramid + ((size_t)n * p.n_pool + k) * plane + (size_t)gy * W;
+                if (want_pyr) {
+                    float* dst = p.pyramid + ((size_t)n * np + p.ps.chan[k]) * plane + (size_t)gy * W;
 #pragma unroll
                     for (int i = 0; i < LH; ++i) {
                         const int c = c0 + i, gx = gxb + i;
-                        if (c >= 4 && c < TW + 4 && gx < W) dst[gx] = m[i];
+                        if (c >= 2 && c < TW + 2 && gx < W) dst[gx] = m[i];
                     }
                 }
-                const float* w0 = s_w1 + k;
+                const u64 m01 = pack2(m[0], m[1]), m23 = pack2(m[2], m[3]);
+                const ulonglong2* wk = reinterpret_cast<const ulonglong2*>(s_w1d + (size_t)k * NF * 2);
 #pragma unroll
-                for (int j = 0; j < NF; ++j) {
-                    const float w = w0[j * p.n_pool];
-#pragma unroll
-                    for (int i = 0; i < LH; ++i) acc[j][i] = fmaf(w, m[i], acc[j][i]);
+                for (int jj = 0; jj < NF / 2; ++jj) {
+                    const ulonglong2 w2 = wk[jj];
+                    acc[2 * jj][0] = ffma2(w2.x, m01, acc[2 * jj][0]);
+                    acc[2 * jj][1] = ffma2(w2.x, m23, acc[2 * jj][1]);
+                    acc[2 * jj + 1][0] = ffma2(w2.y, m01, acc[2 * jj + 1][0]);
+                    acc[2 * jj + 1][1] = ffma2(w2.y, m23, acc[2 * jj + 1][1]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < NF; ++j)
-#pragma unroll
-                for (int i = 0; i < LH; ++i) acc[j][i] = leaky(acc[j][i], slope);
+            for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(acc[j][0], slope2); acc[j][1] = leaky01x2(acc[j][1], slope2); }
 
             for (int l = 1; l < p.n_conv; ++l) {
-                const float* wl = s_w1 + NF * p.n_pool + (l - 1) * NF * NF;
-                float nxt[NF][LH];
+                const ulonglong2* wl = reinterpret_cast<const ulonglong2*>(s_w1d + (size_t)(NF * np + (l - 1) * NF * NF) * 2);
+                u64 nxt[NF][2];
 #pragma unroll
-                for (int j = 0; j < NF; ++j) {
-                    const float4 wa = *reinterpret_cast<const float4*>(wl + j * NF);
-                    const float4 wb = *reinterpret_cast<const float4*>(wl + j * NF + 4);
+                for (int k = 0; k < NF; ++k) {
 #pragma unroll
-                    for (int i = 0; i < LH; ++i) {
-                        float a = wa.x * acc[0][i];
-                        a = fmaf(wa.y, acc[1][i], a);
-                        a = fmaf(wa.z, acc[2][i], a);
-                        a = fmaf(wa.w, acc[3][i], a);
-                        a = fmaf(wb.x, acc[4][i], a);
-                        a = fmaf(wb.y, acc[5][i], a);
-                        a = fmaf(wb.z, acc[6][i], a);
-                        a = fmaf(wb.w, acc[7][i], a);
-                        nxt[j][i] = leaky(a, slope);
+                    for (int jj = 0; jj < NF / 2; ++jj) {
+                        const ulonglong2 w2 = wl[k * (NF / 2) + jj];
+                        if (k == 0) {
+                            nxt[2 * jj][0] = fmul2(w2.x, acc[0][0]);
+                            nxt[2 * jj][1] = fmul2(w2.x, acc[0][1]);
+                            nxt[2 * jj + 1][0] = fmul2(w2.y, acc[0][0]);
+                            nxt[2 * jj + 1][1] = fmul2(w2.y, acc[0][1]);
+                        } else {
+                            nxt[2 * jj][0] = ffma2(w2.x, acc[k][0], nxt[2 * jj][0]);
+                            nxt[2 * jj][1] = ffma2(w2.x, acc[k][1], nxt[2 * jj][1]);
+                            nxt[2 * jj + 1][0] = ffma2(w2.y, acc[k][0], nxt[2 * jj + 1][0]);
+                            nxt[2 * jj + 1][1] = ffma2(w2.y, acc[k][1], nxt[2 * jj + 1][1]);
+                        }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < NF; ++j)
-#pragma unroll
-                    for (int i = 0; i < LH; ++i) acc[j][i] = nxt[j][i];
+                for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(nxt[j][0], slope2); acc[j][1] = leaky01x2(nxt[j][1], slope2); }
             }
-            // zero padding of the 3x3 conv: pixels outside the image contribute 0
-            bool inb[LH];
+            // Q -> bf16 hi/lo chunk planes; pixels outside the image are the zero padding of the 3x3 conv
+            float q[NF][LH];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) { unpack2(acc[j][0], q[j][0], q[j][1]); unpack2(acc[j][1], q[j][2], q[j][3]); }
+            const bool row_in = (unsigned)gy < (unsigned)H;
 #pragma unroll
             for (int i = 0; i < LH; ++i) {
-                const int gx = gxb + i;
-                inb[i] = row_in && gx >= 0 && gx < W;
-            }
+                const bool inb = row_in && (unsigned)(gxb + i) < (unsigned)W;
+                uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                float4 t;
-                t.x = inb[0] ? acc[j][0] : 0.f;
-                t.y = inb[1] ? acc[j][1] : 0.f;
-                t.z = inb[2] ? acc[j][2] : 0.f;
-                t.w = inb[3] ? acc[j][3] : 0.f;
-                *reinterpret_cast<float4*>(s_cin + (j * PH + pr) * PW + c0) = t;
-                if (LH == 8) {
-                    float4 u;
-                    u.x = inb[4 % LH] ? acc[j][4 % LH] : 0.f;
-                    u.y = inb[5 % LH] ? acc[j][5 % LH] : 0.f;
-                    u.z = inb[6 % LH] ? acc[j][6 % LH] : 0.f;
-                    u.w = inb[7 % LH] ? acc[j][7 % LH] : 0.f;
-                    *reinterpret_cast<float4*>(s_cin + (j * PH + pr) * PW + c0 + 4) = u;
+                for (int jp = 0; jp < 4; ++jp) {
+                    split_trunc(q[2 * jp][i], q[2 * jp + 1][i], hi[jp], lo[jp]);
+                    hi[jp] = inb ? hi[jp] : 0u;
+                    lo[jp] = inb ? lo[jp] : 0u;
                 }
-            }
-            for (int c = 0; c < p.C_in; ++c) {
-                const float* src = xin + (size_t)c * plane + (size_t)gy * W;
-#pragma unroll
-                for (int i = 0; i < LH; ++i)
-                    s_cin[((NF + c) * PH + pr) * PW + c0 + i] = inb[i] ? __ldg(src + gxb + i) : 0.f;
+                s_qhi[pr * PW + c0 + i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                s_qlo[pr * PW + c0 + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
     }
     __syncthreads();
 
-    // ---- 4. 3x3 conv over [q(8), x(C_in)] + LeakyReLU, 4 pixels x 8 filters per thread -----------
+    // ---- D. 3x3 conv on mma.sync (bf16 x3 split), LeakyReLU, NCHW stores ---------------------------------------------
     {
-        constexpr int NSX = TW / 4;
-        const bool vec_ok = (W % 4 == 0);
-        for (int s = tid; s < TH * NSX; s += NT) {
-            const int oy = s / NSX, ox = (s - oy * NSX) * 4;
-            const int gy = y0 + oy, gx = x0 + ox;
-            if (gy >= H || gx >= W) continue;
-            float acc[NF][4];
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int LR = TH / 2;                 // output rows per warp
+        const int cb = warp & 3, rg = warp >> 2;  // 16-column block, row group
+        const int g = lane >> 2, t = lane & 3;
+        uint2 bf[6][2];
 #pragma unroll
-            for (int j = 0; j < NF; ++j)
+        for (int ks = 0; ks < 6; ++ks) {
+            bf[ks][0] = s_wB[(ks * 2 + 0) * 32 + lane];
+            bf[ks][1] = s_wB[(ks * 2 + 1) * 32 + lane];
+        }
+        float acc[LR][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-            for (int c = 0; c < n_cin_tot; ++c) {
+        for (int i = 0; i < LR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        // ldmatrix row addresses: matrix m = lane / 8 -> pixel half (m & 1), chunk (m >> 1); row = lane & 7
+        const int mrow = ((lane >> 3) & 1) * 8 + (lane & 7);
+        const int col_s0 = 16 * cb + mrow + 1 + (lane >> 4);  // k-step half 0: dx = 0 (chunk A), dx = 1 (chunk B)
+        const int col_s1 = 16 * cb + mrow + 1 + 2;            // k-step half 1, chunk A: dx = 2
+        // raw-channel fragment: lane t holds slots (2t, 2t+1)
+        int xoff;
+        uint32_t xmask;
+        if (C_in > 1) { xoff = t < 3 ? t : 0; xmask = t < 3 ? 0xFFFFFFFFu : 0u; }
+        else          { xoff = t < 2 ? 2 * t : 0; xmask = t == 0 ? 0xFFFFFFFFu : (t == 1 ? 0x0000FFFFu : 0u); }
+        const int col_x = 16 * cb + g + 1 + xoff;
+        const uint32_t q_row0 = (uint32_t)(LR * rg * PW) * 16u;
+        const uint32_t a_s0h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s0 * 16u, a_s0l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s0 * 16u;
+        const uint32_t a_s1h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s1 * 16u, a_s1l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s1 * 16u;
+        const uint2* xrow = s_xc + LR * rg * PW + col_x;
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const float* row = s_cin + (c * PH + oy + dy) * PW + ox + 3;  // pyramid col of (ox - 1)
-                    float in[6];
-                    in[0] = row[0];
-                    const float4 t = *reinterpret_cast<const float4*>(row + 1);
-                    in[1] = t.x; in[2] = t.y; in[3] = t.z; in[4] = t.w;
-                    in[5] = row[5];
-                    const float* wr = s_w3 + (c * 3 + dy) * 3 * NF;
+        for (int qr = 0; qr < LR + 2; ++qr) {
+            uint32_t a0h[4], a0l[4], a1h[4], a1l[4];
+            ldsm_x4(a_s0h + (uint32_t)(qr * PW * 16), a0h);
+            ldsm_x4(a_s0l + (uint32_t)(qr * PW * 16), a0l);
+            ldsm_x2(a_s1h + (uint32_t)(qr * PW * 16), a1h[0], a1h[1]);
+            ldsm_x2(a_s1l + (uint32_t)(qr * PW * 16), a1l[0], a1l[1]);
+            const uint2 xa = xrow[qr * PW], xb = xrow[qr * PW + 8];
+            a1h[2] = xa.x & xmask; a1l[2] = xa.y & xmask;
+            a1h[3] = xb.x & xmask; a1l[3] = xb.y & xmask;
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float4 wa = *reinterpret_cast<const float4*>(wr + dx * NF);
-                        const float4 wb = *reinterpret_cast<const float4*>(wr + dx * NF + 4);
-                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                        for (int j = 0; j < NF; ++j)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(wv[j], in[i + dx], acc[j][i]);
-                    }
+            for (int dy = 0; dy < 3; ++dy) {
+                const int li = qr - dy;
+                if (li >= 0 && li < LR) {
+                    hmma(acc[li], a0h, bf[2 * dy][0].x, bf[2 * dy][0].y);
+                    hmma(acc[li], a0l, bf[2 * dy][0].x, bf[2 * dy][0].y);
+                    hmma(acc[li], a0h, bf[2 * dy][1].x, bf[2 * dy][1].y);
+                    hmma(acc[li], a1h, bf[2 * dy + 1][0].x, bf[2 * dy + 1][0].y);
+                    hmma(acc[li], a1l, bf[2 * dy + 1][0].x, bf[2 * dy + 1][0].y);
+                    hmma(acc[li], a1h, bf[2 * dy + 1][1].x, bf[2 * dy + 1][1].y);
                 }
             }
-            float* dst = p.out + ((size_t)n * NF) * plane + (size_t)gy * W + gx;
+        }
+        // epilogue: c0,c1 = (pixel g, filters 2t, 2t+1), c2,c3 = (pixel g + 8, same filters)
+        const int gxa = x0 + 16 * cb + g;
+        const bool in_a = gxa < W, in_b = gxa + 8 < W;
+        float* d0 = p.out + ((size_t)n * NF + 2 * t) * plane + (size_t)(y0 + LR * rg) * W + gxa;
 #pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                float4 t;
-                t.x = leaky(acc[j][0], p.slope);
-                t.y = leaky(acc[j][1], p.slope);
-                t.z = leaky(acc[j][2], p.slope);
-                t.w = leaky(acc[j][3], p.slope);
-                float* d = dst + (size_t)j * plane;
-                if (vec_ok) {
-                    *reinterpret_cast<float4*>(d) = t;
-                } else {
-                    d[0] = t.x;
-                    if (gx + 1 < W) d[1] = t.y;
-                    if (gx + 2 < W) d[2] = t.z;
-                    if (gx + 3 < W) d[3] = t.w;
-                }
+        for (int li = 0; li < LR; ++li) {
+            if (y0 + LR * rg + li < H) {
+                if (in_a) { d0[0] = leaky01(acc[li][0], slope); d0[plane] = leaky01(acc[li][1], slope); }
+                if (in_b) { d0[8] = leaky01(acc[li][2], slope); d0[plane + 8] = leaky01(acc[li][3], slope); }
             }
+            d0 += W;
         }
     }
 }
 
-template <int TH, int TW, int R, int LV, int LH, int NT>
-static int launch_s2d(S2DParams& p, cudaStream_t stream) {
-    constexpr int PH = TH + 2, PW = TW + 8, ZH = PH + 2 * R, ZW = PW + 2 * R;
-    const int n_cin_tot = S2D_NF + p.C_in;
-    const int n_w1 = S2D_NF * p.n_pool + (p.n_conv - 1) * S2D_NF * S2D_NF;
-    const int n_w3 = n_cin_tot * 9 * S2D_NF;
-    const size_t tail = (size_t)2 * ZH * ZW > (size_t)n_cin_tot * PH * PW ? (size_t)2 * ZH * ZW : (size_t)n_cin_tot * PH * PW;
-    const size_t smem = sizeof(float) * (((n_w1 + 3) & ~3) + ((n_w3 + 3) & ~3) + (size_t)p.n_pool * PH * ZW + tail);
-    KB_CHECK_ARG(smem <= 227 * 1024, "s2d: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
-    auto kern = s2d_fused_kernel<TH, TW, R, LV, LH, NT>;
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+// 3-D tiled tensor map over x viewed as [N*C_in][H][W] fp32, box = {bw, bh, 1}, out-of-bounds elements read as zero
+bool make_map(CUtensorMap* tm, const float* x, int NC, int H, int W, int bw, int bh) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    if ((W & 3) || ((uintptr_t)x & 15) || bw > 256 || bh > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NC};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int R>
+int launch_fast(FastParams& p, cudaStream_t stream) {
+    const Layout L = make_layout(R, p.ps.n_pool, p.n_conv);
+    alignas(64) CUtensorMap tm_z, tm_x1;
+    memset(&tm_z, 0, sizeof(tm_z));
+    memset(&tm_x1, 0, sizeof(tm_x1));
+    static const bool no_tma = getenv("KBNET_S2D_NO_TMA") != nullptr;  // debugging aid: stage the tile with plain loads
+    p.use_tma = !no_tma && make_map(&tm_z, p.x, p.N * p.C_in, p.H, p.W, PW + 2 * R + 4, PHV + 2 * R) &&
+                (p.C_in == 1 || make_map(&tm_x1, p.x, p.N * p.C_in, p.H, p.W, XP, PH));
+    auto kern = s2d_fused_kernel<R>;
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     p.tiles_x = cdiv(p.W, TW);
     p.tiles_y = cdiv(p.H, TH);
     const long long grid = (long long)p.tiles_x * p.tiles_y * p.N;
     KB_CHECK_ARG(grid > 0 && grid < (1ll << 31), "s2d: grid too large");
-    kern<<<(unsigned)grid, NT, smem, stream>>>(p);
+    kern<<<(unsigned)grid, NT, L.total, stream>>>(p, tm_z, tm_x1);
+    KB_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// canonical pool order; false if the configuration is outside the fast path (duplicate sizes within a group)
+bool make_pool_spec(const int* min_sizes, int n_min, const int* max_sizes, int n_max, PoolSpec* ps) {
+    memset(ps, 0, sizeof(*ps));
+    ps->n_pool = n_min + n_max;
+    ps->n_min = n_min;
+    int k = 0;
+    for (int grp = 0; grp < 2; ++grp) {
+        const int* sizes = grp ? max_sizes : min_sizes;
+        const int cnt = grp ? n_max : n_min, base = grp ? n_min : 0;
+        for (int r = 1; r <= 16; ++r)
+            for (int i = 0; i < cnt; ++i)
+                if (sizes[i] / 2 == r) {
+                    unsigned& mask = grp ? ps->max_mask : ps->min_mask;
+                    if (mask & (1u << r)) return false;
+                    mask |= 1u << r;
+                    ps->radius[k] = r;
+                    ps->chan[k] = base + i;
+                    ++k;
+                    int& rmax = grp ? ps->rmax_max : ps->rmax_min;
+                    rmax = r;
+                }
+    }
+    return k == ps->n_pool;
+}
+
+// Is this configuration on the packed fast path?  (C_in <= 2, distinct pool sizes, 0 <= slope <= 1, n_filter == 8 and a
+// shared-memory footprint that lets two CTAs share an SM.)  Everything else runs the generic exact-fp32 kernel.
+bool fast_path(int C_in, const int* min_sizes, int n_min, const int* max_sizes, int n_max, int n_conv, int n_filter, float slope,
+               PoolSpec* ps, int* R_out) {
+    if (n_filter != NF || n_conv < 1 || n_conv > MAX_CONV || n_min < 0 || n_max < 0 || n_min + n_max < 1 || n_min + n_max > MAX_POOL)
+        return false;
+    for (int k = 0; k < n_min + n_max; ++k) {
+        const int s = k < n_min ? min_sizes[k] : max_sizes[k - n_min];
+        if (s < 3 || !(s & 1) || s > 33) return false;
+    }
+    if (!make_pool_spec(min_sizes, n_min, max_sizes, n_max, ps)) return false;
+    const int rmax = ps->rmax_min > ps->rmax_max ? ps->rmax_min : ps->rmax_max;
+    const int R = rmax <= 4 ? 4 : (rmax <= 8 ? 8 : 16);
+    *R_out = R;
+    return C_in >= 1 && C_in <= 2 && slope >= 0.f && slope <= 1.f && make_layout(R, ps->n_pool, n_conv).total <= SMEM_2CTA;
+}
+
+}  // namespace
+
+size_t s2d_wpack_bytes(int C_in, const int* min_sizes, int n_min, const int* max_sizes, int n_max, int n_conv, int n_filter, float slope) {
+    PoolSpec ps;
+    int R;
+    if (!min_sizes || !max_sizes || !fast_path(C_in, min_sizes, n_min, max_sizes, n_max, n_conv, n_filter, slope, &ps, &R)) return 0;
+    return (size_t)w1d_bytes(ps.n_pool, n_conv) + WB_BYTES;
+}
+
+int s2d_pack_weights(const float* const* w_1x1, int n_conv, const float* w_3x3, int C_in, const int* min_sizes, int n_min,
+                     const int* max_sizes, int n_max, void* wpack, cudaStream_t stream) {
+    KB_CHECK_ARG(w_1x1 && w_3x3 && wpack, "s2d pack: null pointer argument");
+    KB_CHECK_ARG(n_conv >= 1 && n_conv <= MAX_CONV && C_in >= 1 && n_min >= 0 && n_max >= 0 && n_min + n_max >= 1 &&
+                 n_min + n_max <= MAX_POOL, "s2d pack: bad configuration");
+    KB_CHECK_ARG(((uintptr_t)wpack & 15) == 0, "s2d pack: wpack must be 16-byte aligned");
+    PoolSpec ps;
+    KB_CHECK_ARG(C_in <= 2 && make_pool_spec(min_sizes, n_min, max_sizes, n_max, &ps),
+                 "s2d pack: configuration is outside the packed fast path (input_channels > 2 or duplicate pool sizes)");
+    WeightSrc ws;
+    memset(&ws, 0, sizeof(ws));
+    for (int l = 0; l < n_conv; ++l) {
+        KB_CHECK_ARG(w_1x1[l], "s2d pack: w_1x1[%d] is null", l);
+        ws.w1x1[l] = w_1x1[l];
+    }
+    ws.w3x3 = w_3x3; ws.n_conv = n_conv; ws.n_pool = ps.n_pool; ws.C_in = C_in;
+    for (int k = 0; k < MAX_POOL; ++k) ws.chan[k] = ps.chan[k];
+    s2d_pack_weights_kernel<<<1, 256, 0, stream>>>(ws, (uint8_t*)wpack);
     KB_CUDA(cudaGetLastError());
     count_launch();
     return 0;
 }
 
 int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
-                int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, float neg_slope,
+                int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack, float neg_slope,
                 float* out, float* pyramid, cudaStream_t stream) {
     if (N == 0) return 0;
     KB_CHECK_ARG(x && out && w_3x3 && w_1x1, "s2d: null pointer argument");
     KB_CHECK_ARG(N >= 0 && H > 0 && W > 0, "s2d: bad shape N=%d H=%d W=%d", N, H, W);
-    KB_CHECK_ARG(C_in >= 1 && C_in <= S2D_MAX_CIN, "s2d: input_channels=%d unsupported (1..%d)", C_in, S2D_MAX_CIN);
-    KB_CHECK_ARG(n_filter == S2D_NF, "s2d: n_filter=%d unsupported (only %d)", n_filter, S2D_NF);
-    KB_CHECK_ARG(n_conv >= 1 && n_conv <= S2D_MAX_CONV, "s2d: n_convolution=%d unsupported (1..%d)", n_conv, S2D_MAX_CONV);
-    KB_CHECK_ARG(n_min >= 0 && n_max >= 0 && n_min + n_max >= 1 && n_min + n_max <= S2D_MAX_POOL,
-                 "s2d: %d pool sizes unsupported (1..%d)", n_min + n_max, S2D_MAX_POOL);
-    if (N == 0) return 0;
-    S2DParams p;
-    p.x = x; p.out = out; p.pyramid = pyramid;
-    p.N = N; p.C_in = C_in; p.H = H; p.W = W;
-    p.n_pool = n_min + n_max; p.n_min = n_min;
-    p.min_mask = p.max_mask = 0; p.rmax_min = p.rmax_max = 0;
-    for (int k = 0; k < S2D_MAX_POOL; ++k) p.radius[k] = 0;
-    for (int k = 0; k < p.n_pool; ++k) {
+    KB_CHECK_ARG(n_filter == NF, "s2d: n_filter=%d unsupported (only %d)", n_filter, NF);
+    KB_CHECK_ARG(n_conv >= 1 && n_conv <= MAX_CONV, "s2d: n_convolution=%d unsupported (1..%d)", n_conv, MAX_CONV);
+    KB_CHECK_ARG(n_min >= 0 && n_max >= 0 && n_min + n_max >= 1 && n_min + n_max <= MAX_POOL,
+                 "s2d: %d pool sizes unsupported (1..%d)", n_min + n_max, MAX_POOL);
+    for (int k = 0; k < n_min + n_max; ++k) {
         const int s = k < n_min ? min_sizes[k] : max_sizes[k - n_min];
         KB_CHECK_ARG(s >= 3 && (s & 1) && s <= 33, "s2d: pool size %d unsupported (odd, 3..33)", s);
-        const int r = s / 2;
-        p.radius[k] = r;
-        if (k < n_min) { p.min_mask |= 1u << r; if (r > p.rmax_min) p.rmax_min = r; }
-        else           { p.max_mask |= 1u << r; if (r > p.rmax_max) p.rmax_max = r; }
     }
-    for (int l = 0; l < S2D_MAX_CONV; ++l) p.w1x1[l] = l < n_conv ? w_1x1[l] : nullptr;
-    for (int l = 0; l < n_conv; ++l) KB_CHECK_ARG(p.w1x1[l], "s2d: w_1x1[%d] is null", l);
-    p.n_conv = n_conv; p.w3x3 = w_3x3; p.slope = neg_slope;
-    const int rmax = p.rmax_min > p.rmax_max ? p.rmax_min : p.rmax_max;
-    if (rmax <= 4) return launch_s2d<16, 64, 4, 9, 4, 256>(p, stream);
-    if (rmax <= 8) return launch_s2d<16, 64, 8, 9, 4, 256>(p, stream);
-    return launch_s2d<16, 64, 16, 9, 4, 256>(p, stream);
+    for (int l = 0; l < n_conv; ++l) KB_CHECK_ARG(w_1x1[l], "s2d: w_1x1[%d] is null", l);
+    FastParams p;
+    memset(&p, 0, sizeof(p));
+    int R = 0;
+    if (!fast_path(C_in, min_sizes, n_min, max_sizes, n_max, n_conv, n_filter, neg_slope, &p.ps, &R)) {
+        KB_CHECK_ARG(wpack == nullptr, "s2d: packed weights given for a configuration outside the packed fast path");
+        return s2d_generic_forward(x, N, C_in, H, W, min_sizes, n_min, max_sizes, n_max, w_1x1, n_conv, n_filter, w_3x3, neg_slope,
+                                   out, pyramid, stream);
+    }
+    KB_CHECK_ARG(((uintptr_t)wpack & 15) == 0, "s2d: wpack must be 16-byte aligned");
+    p.x = x; p.out = out; p.pyramid = pyramid;
+    p.N = N; p.C_in = C_in; p.H = H; p.W = W;
+    for (int l = 0; l < n_conv; ++l) p.ws.w1x1[l] = w_1x1[l];
+    p.ws.w3x3 = w_3x3; p.ws.n_conv = n_conv; p.ws.n_pool = p.ps.n_pool; p.ws.C_in = C_in;
+    for (int k = 0; k < MAX_POOL; ++k) p.ws.chan[k] = p.ps.chan[k];
+    p.n_conv = n_conv; p.wpack = (const uint8_t*)wpack; p.slope = neg_slope;
+    if (R == 4) return launch_fast<4>(p, stream);
+    if (R == 8) return launch_fast<8>(p, stream);
+    return launch_fast<16>(p, stream);
 }
 
 }  // namespace kbnet

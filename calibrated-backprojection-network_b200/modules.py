@@ -223,9 +223,23 @@ class SparseToDensePool(torch.nn.Module):
         mins = (ctypes.c_int * max(n_min, 1))(*self.min_pool_sizes)
         maxs = (ctypes.c_int * max(n_max, 1))(*self.max_pool_sizes)
         w1p = (ctypes.c_void_p * max(len(w1), 1))(*[t.data_ptr() for t in w1])
+        # packed weight image for the fused kernel, cached until a weight changes (value, storage or device)
+        key = tuple((t.data_ptr(), t._version) for t in w1 + [w3]) + (c, self.negative_slope)
+        cache = self.__dict__.get('_kbnet_s2d_pack')
+        if cache is None or cache[0] != key:
+            nbytes = lib.kbnet_s2d_wpack_bytes(c, mins, n_min, maxs, n_max, len(w1), self.n_filter, self.negative_slope)
+            pack = None
+            if nbytes:
+                pack = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    rc = lib.kbnet_s2d_pack_weights(w1p, len(w1), w3.data_ptr(), c, mins, n_min, maxs, n_max, pack.data_ptr(), _stream(dev))
+                _lib.check(rc, 'kbnet_s2d_pack_weights')
+            cache = (key, pack)
+            self.__dict__['_kbnet_s2d_pack'] = cache
+        pack = cache[1]
         with torch.cuda.device(dev):
             rc = lib.kbnet_s2d_forward(x.data_ptr(), n, c, h, w, mins, n_min, maxs, n_max, w1p, len(w1), self.n_filter,
-                                       w3.data_ptr(), self.negative_slope, out.data_ptr(),
+                                       w3.data_ptr(), pack.data_ptr() if pack is not None else None, self.negative_slope, out.data_ptr(),
                                        pyr.data_ptr() if pyr is not None else None, _stream(dev))
         _lib.check(rc, 'kbnet_s2d_forward')
         return (out, pyr) if return_pyramid else out

@@ -49,14 +49,26 @@ unsigned long long kbnet_launch_count(void);
  *                                 as the reference ctor does at :2112-2118); size <= 33
  *   w_1x1    HOST array of n_conv DEVICE pointers: w_1x1[0] is [n_filter, n_min+n_max], others [n_filter, n_filter]
  *   w_3x3    [n_filter, n_filter + C_in, 3, 3]
+ *   wpack    optional (may be NULL): the weights pre-packed by kbnet_s2d_pack_weights() into the shared-memory image the
+ *            fused kernel loads with one bulk copy (saves every CTA re-deriving it from the raw tensors).  Must be NULL
+ *            when kbnet_s2d_wpack_bytes() returns 0 for the configuration.  Re-pack whenever the weight values change.
  *   out      [N, n_filter, H, W]
  *   pyramid  optional (may be NULL) [N, n_min+n_max, H, W]: the pool pyramid, for bit-exact checks
  * Supported: n_filter == 8, 1 <= n_conv <= 8, 1 <= n_min+n_max <= 16, 1 <= C_in <= 8.
+ * Fast path (TMA tile staging, tensor-core 3x3): C_in <= 2, distinct sizes within each list, 0 <= neg_slope <= 1;
+ * other configurations run an exact-fp32 CUDA-core kernel with the same fusion.
  */
 int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W,
                       const int* min_sizes, int n_min, const int* max_sizes, int n_max,
-                      const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3,
+                      const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack,
                       float neg_slope, float* out, float* pyramid, void* stream);
+
+/* Size of the packed S2D weight image for this configuration, or 0 if the configuration is outside the fast path
+ * (then pass wpack = NULL).  `wpack` must be 16-byte aligned device memory. */
+size_t kbnet_s2d_wpack_bytes(int C_in, const int* min_sizes, int n_min, const int* max_sizes, int n_max,
+                             int n_conv, int n_filter, float neg_slope);
+int    kbnet_s2d_pack_weights(const float* const* w_1x1, int n_conv, const float* w_3x3, int C_in,
+                              const int* min_sizes, int n_min, const int* max_sizes, int n_max, void* wpack, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CalibratedBackprojectionBlock.forward -- replaces reference src/net_utils.py:1343-1371

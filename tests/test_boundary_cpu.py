@@ -41,7 +41,7 @@ def test_library_is_sm100a_and_has_no_torch_dependency():
 
 def test_bad_arguments_return_error_codes_not_crashes():
     lib = _lib.load()
-    rc = lib.kbnet_s2d_forward(None, 1, 2, 8, 8, None, 0, None, 0, None, 1, 8, None, 0.2, None, None, None)
+    rc = lib.kbnet_s2d_forward(None, 1, 2, 8, 8, None, 0, None, 0, None, 1, 8, None, None, 0.2, None, None, None)
     assert rc != 0 and b'null' in lib.kbnet_last_error()
     with pytest.raises(RuntimeError, match='kbnet_b200 .* failed'):
         _lib.check(rc, 'kbnet_s2d_forward')
