@@ -7,8 +7,10 @@ namespace kbnet {
 
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;  // statistics only (atomic increments)
+static unsigned long long g_launches_v2 = 0;
 
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+void count_launch_v2() { __atomic_fetch_add(&g_launches_v2, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -51,6 +53,7 @@ int kbnet_version(void) { return KBNET_B200_VERSION; }
 const char* kbnet_last_error(void) { return g_err; }
 
 unsigned long long kbnet_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+unsigned long long kbnet_tma_engine_launch_count(void) { return __atomic_load_n(&g_launches_v2, __ATOMIC_RELAXED); }
 
 int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
                       int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack,
@@ -100,6 +103,14 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
     KB_CHECK_ARG(image_stride_n >= C_i * plane && depth_stride_n >= C_d * plane && (!fused || fused_stride_n >= C_f * plane),
                  "kb: input stride_n smaller than C*H*W");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    KB_CHECK_ARG(out_image_stride_n >= (long long)F_i * Ho * Wo && out_depth_stride_n >= (long long)F_d * Ho * Wo &&
+                 out_fused_stride_n >= (long long)F_f * Ho * Wo, "kb: output stride_n smaller than F*Ho*Wo");
+    // the whole block as ONE fused launch (conv_tma.cu) whenever the tensors can be described to TMA
+    if (wpack_image && kb_fused_supported(image, image_stride_n, depth, depth_stride_n, fused, fused_stride_n, coordinates, C_i, C_d, C_f, H, W,
+                                          F_i, F_d, F_f))
+        return kb_fused_launch(image, image_stride_n, depth, depth_stride_n, fused, fused_stride_n, coordinates, kinv, N, C_i, C_d, C_f, H, W,
+                               w_proj, wpack_image, F_i, wpack_depth, F_d, wpack_fused, F_f, neg_slope, out_image, out_image_stride_n,
+                               out_depth, out_depth_stride_n, out_fused, out_fused_stride_n, stream);
     const size_t need = kbnet_kb_workspace_bytes(N, C_i, C_d, C_f, H, W, F_i, F_d, F_f);
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("kb: workspace of %zu bytes needed, %zu given", need, workspace_bytes);

@@ -12,6 +12,7 @@ namespace kbnet {
 // ---- thread-local error message (no global mutable state shared between threads) ---------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);  // statistics for kbnet_launch_count()
+void count_launch_v2();         // ... and for kbnet_tma_engine_launch_count()
 
 #define KB_CHECK_ARG(cond, ...)                         \
     do {                                                \

@@ -69,8 +69,19 @@ bool conv_umma_supported(const ConvParams& p);
 int conv_umma_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
 size_t conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize);
 int conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, cudaStream_t stream);
+// second-generation engine (conv_tma.cu): persistent, TMA-fed; takes the same packed weights as conv_umma.cu
+bool conv_v2_supported(const ConvParams& p);
+int conv_v2_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
+bool kb_fused_supported(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
+                        const float* coordinates, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);
+int kb_fused_launch(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
+                    const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_proj,
+                    const void* wpack_image, int F_i, const void* wpack_depth, int F_d, const void* wpack_fused, int F_f, float slope,
+                    float* out_image, long long out_image_sn, float* out_depth, long long out_depth_sn, float* out_fused, long long out_fused_sn,
+                    cudaStream_t stream);
 inline int conv_launch(const ConvParams& p, const void* wpack, cudaStream_t stream) {
-    return wpack ? conv_umma_launch(p, wpack, stream) : conv_direct_launch(p, stream);
+    if (!wpack) return conv_direct_launch(p, stream);
+    return conv_v2_supported(p) ? conv_v2_launch(p, wpack, stream) : conv_umma_launch(p, wpack, stream);
 }
 int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int N, int C, int H, int W, int Ho, int Wo, float slope, float* z,
                      cudaStream_t stream);

@@ -1,0 +1,934 @@
+// Tensor-core convolution engine, second generation ("v2"): persistent, TMA-fed, warp-specialised, table-driven.
+//
+//   out_j[n, f, oy, ox] = act( sum_{c, ky, kx} w_j[f, c, ky, kx] * in_j[n, c, oy*s - pad + ky, ox*s - pad + kx] )     j = 0 .. n_convs-1
+//
+// One launch runs a small PROGRAM: a list of K16 stages (two 8-channel chunks each) and, per stage, the convolutions
+// ("uses") that consume it.  A plain convolution is a program with one use per stage; the Calibrated Backprojection block
+// (reference src/net_utils.py:1343-1371) is ONE program in which the image tile is staged once and feeds both conv_image
+// (3x3 stride 2, nine taps) and conv_fused (1x1 stride 2 = the centre tap of the same parity planes), the depth tile
+// feeds conv_depth and -- on the CUDA cores of the converter warps -- z = leaky(w_proj . depth), the camera coordinates
+// are generated from K^-1 in registers, xyz = coordinates * z goes straight into an operand plane, and three accumulators
+// live side by side in TMEM.  No intermediate (coordinates, z, xyz, any torch.cat) ever exists in global memory.
+//
+// Data path per CTA (one CTA per SM, looping over tiles):
+//   HBM --TMA (cp.async.bulk.tensor.4d, fp32 NCHW boxes, zero fill = conv padding)--> raw ring in shared memory
+//       --converter warps (fp32 -> bf16 hi + bf16 lo, transposed to K-major "chunk planes")--> A ring
+//       --tcgen05.mma (one thread; 3x3 taps are row-shifted descriptors of the same plane, no im2col)--> TMEM accumulators
+//       --epilogue warps (tcgen05.ld, LeakyReLU, coalesced NCHW stores)--> HBM,
+//   with the accumulator double-buffered in TMEM so that the epilogue of tile i overlaps the main loop of tile i+1, and
+//   the weights streamed as pre-packed bf16 hi/lo tiles through their own bulk-copy ring.
+//
+// Arithmetic: a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation (16 mantissa bits per operand, ~1e-5
+// relative).  When the filter count is small the three products cost two MMAs: B' = [b_hi | b_lo] doubles N
+// (free below N ~ 48, profiles/r01_umma_probe.md) and the epilogue adds the two column groups ("dual" mode).
+//
+// Roles (512 threads): warps 0-7 converters | warp 8 activation TMA | warp 9 weight TMA | warp 10 MMA issuer + TMEM
+// allocator | warps 12-15 epilogue (TMEM lane quarter = warp % 4).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "conv_common.cuh"
+#include "umma.cuh"
+
+namespace kbnet {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int V2_MAX_STAGES = 72;
+constexpr int V2_MAX_CONVS = 3;
+constexpr int V2_MAX_MAPS = 4;
+constexpr int V2_CONV_WARPS = 8;
+constexpr int V2_CONV_THREADS = V2_CONV_WARPS * 32;
+constexpr int V2_THREADS = 512;
+constexpr int V2_MAX_RAW = 6, V2_MAX_A = 3, V2_MAX_W = 8;
+constexpr int V2_HEADER = 2048;
+constexpr int V2_SMEM_LIMIT = 227 * 1024;
+constexpr int V2_MAX_ZC = 256;  // channels of the z projection
+
+enum { G_S1K3 = 0, G_S1K1 = 1, G_S2K3 = 2, G_S2K1 = 3 };
+enum { CK_NONE = 0, CK_TMA = 1, CK_TMA_P0 = 2, CK_COORDS = 3, CK_XYZ = 4, CK_XYZ_T = 5 };
+enum { TAPS_ALL = 0, TAPS_CENTER = 1 };
+
+struct V2Chunk {
+    uint8_t kind, tmap, nch, cls;  // cls: 0 = source at the conv input resolution, 1 = source at half resolution (nearest 2x upsample)
+    uint16_t c0;
+    uint8_t zacc, pad;
+};
+struct V2Use {
+    uint8_t conv, taps, first, pad;
+    uint32_t wtile;  // index of the first weight tile of this (conv, stage) in the conv's packed buffer
+};
+struct V2Stage {
+    V2Chunk ch[2];
+    V2Use use[2];
+    int n_use, pad;
+};
+struct V2Conv {
+    const uint8_t* wpack;  // [tile][hi|lo][chunk 0|1][Npad rows][16 B]   (conv_pack_weights)
+    float* out;
+    long long out_stride_n;
+    int F, Npad, Nsl;  // Nsl = filters per split part
+    int col;           // first TMEM column of this conv inside the column group of one M-block
+    int act, ntaps;
+};
+struct V2Params {
+    V2Stage stage[V2_MAX_STAGES];
+    V2Conv conv[V2_MAX_CONVS];
+    int n_stages, n_convs, geo, dual;
+    int N, Hin, Win, Hout, Wout;
+    int R, TW, P, MB, n_entries, plane_px, n_planes;
+    int tiles_x, tiles_y, n_split;
+    long long n_tiles;
+    int BW[2], BH[2];
+    int raw_bytes, a_bytes, w_bytes;  // bytes per ring slot
+    int n_raw, n_a, n_w;
+    int cols_block, acc_bufs, tmem_cols;
+    float slope;
+    const float* kinv;    // [N, 9]   (CK_COORDS / CK_XYZ)
+    const float* w_proj;  // [C_z]    (zacc)
+    int C_z;
+};
+struct alignas(64) V2Maps {
+    CUtensorMap m[V2_MAX_MAPS];
+};
+
+// barrier slots
+constexpr int B_RAW_FULL = 0, B_RAW_EMPTY = B_RAW_FULL + V2_MAX_RAW, B_A_FULL = B_RAW_EMPTY + V2_MAX_RAW, B_A_EMPTY = B_A_FULL + V2_MAX_A,
+              B_W_FULL = B_A_EMPTY + V2_MAX_A, B_W_EMPTY = B_W_FULL + V2_MAX_W, B_ACC_FULL = B_W_EMPTY + V2_MAX_W, B_ACC_EMPTY = B_ACC_FULL + 2,
+              B_COUNT = B_ACC_EMPTY + 2;
+static_assert(B_COUNT * 8 <= 512, "barrier area");
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void store_split8(uint8_t* hi_dst, uint8_t* lo_dst, const float (&v)[8]) {
+    const uint2 a = split_bf16x2(v[0], v[1]), b = split_bf16x2(v[2], v[3]);
+    const uint2 c = split_bf16x2(v[4], v[5]), d = split_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(a.x, b.x, c.x, d.x);
+    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(a.y, b.y, c.y, d.y);
+}
+
+struct TileCoord {
+    int n, oy0, ox0, split;
+};
+__device__ __forceinline__ TileCoord decode_tile(const V2Params& p, long long tile) {
+    TileCoord t;
+    t.split = (int)(tile % p.n_split);
+    long long r = tile / p.n_split;
+    const int tx = (int)(r % p.tiles_x);
+    r /= p.tiles_x;
+    const int ty = (int)(r % p.tiles_y);
+    t.n = (int)(r / p.tiles_y);
+    t.oy0 = ty * p.R;
+    t.ox0 = tx * p.TW;
+    return t;
+}
+
+template <int GEO>
+__global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ V2Maps maps) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t bar0 = smem_u32(smem);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+    float* s_wz = reinterpret_cast<float*>(smem + 1024);  // z-projection weights, zero padded
+    uint8_t* sRaw = smem + V2_HEADER;
+    uint8_t* sA = sRaw + (size_t)p.n_raw * p.raw_bytes;
+    uint8_t* sW = sA + (size_t)p.n_a * p.a_bytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < V2_MAX_RAW; ++i) { mbar_init(BAR(B_RAW_FULL + i), 1); mbar_init(BAR(B_RAW_EMPTY + i), V2_CONV_WARPS); }
+        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), V2_CONV_WARPS); mbar_init(BAR(B_A_EMPTY + i), 1); }
+        for (int i = 0; i < V2_MAX_W; ++i) { mbar_init(BAR(B_W_FULL + i), 1); mbar_init(BAR(B_W_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACC_FULL + i), 1); mbar_init(BAR(B_ACC_EMPTY + i), 4); }
+        fence_mbar_init();
+    }
+    if (tid < V2_MAX_ZC) s_wz[tid] = (p.w_proj != nullptr && tid < p.C_z) ? __ldg(p.w_proj + tid) : 0.f;
+    if (warp == 10) {
+        tmem_alloc_dyn(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long long tile0 = blockIdx.x, tstep = gridDim.x;
+
+    if (warp < V2_CONV_WARPS) {
+        // =================================================================================================================
+        // converters: raw fp32 tile (shared) -> bf16 hi/lo chunk planes (shared), plus the generated chunks and z
+        // =================================================================================================================
+        constexpr int MAXI = (GEO == G_S2K3 || GEO == G_S2K1) ? 2 : 4;
+        int it_e[MAXI], it_ei[MAXI], it_ej[MAXI], ro0[MAXI], ro1[MAXI];
+        int n_it = 0;
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i) {
+            const int e = tid + i * V2_CONV_THREADS;
+            it_e[i] = e;
+            const int ei = e / p.P, ej = e - ei * p.P;
+            it_ei[i] = ei; it_ej[i] = ej;
+            if (GEO == G_S1K3) { ro0[i] = ei * p.BW[0] + ej + 3; ro1[i] = ((ei + 1) >> 1) * p.BW[1] + ((ej + 1) >> 1) + 3; }
+            else if (GEO == G_S1K1) { ro0[i] = ei * p.BW[0] + ej; ro1[i] = 0; }
+            else if (GEO == G_S2K3) { ro0[i] = (2 * ei) * p.BW[0] + 2 * ej + 2; ro1[i] = 0; }
+            else { ro0[i] = (2 * ei) * p.BW[0] + 2 * ej; ro1[i] = 0; }
+            if (e < p.n_entries) n_it = i + 1;
+        }
+        const int cp0 = p.BW[0] * p.BH[0], cp1 = p.BW[1] * p.BH[1];  // channel pitch of the raw tile (floats)
+        const size_t plane_b = (size_t)p.plane_px * 16;
+        uint32_t raw_it = 0, a_it = 0;
+        for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
+            const TileCoord tc = decode_tile(p, tile);
+            float zacc[MAXI];
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i) zacc[i] = 0.f;
+            float kv[9];
+            if (p.kinv != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) kv[i] = __ldg(p.kinv + (size_t)tc.n * 9 + i);
+            }
+            for (int s = 0; s < p.n_stages; ++s) {
+                const V2Stage& st = p.stage[s];
+                const int aslot = a_it % p.n_a;
+                mbar_wait(BAR(B_A_EMPTY + aslot), ((a_it / p.n_a) & 1u) ^ 1u);
+                uint8_t* A = sA + (size_t)aslot * p.a_bytes;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const V2Chunk ch = st.ch[h];
+                    const int kind = ch.kind;
+                    const bool is_tma = kind == CK_TMA || kind == CK_TMA_P0 || kind == CK_XYZ_T;
+                    const float* raw = nullptr;
+                    int rslot = 0;
+                    if (is_tma) {
+                        rslot = raw_it % p.n_raw;
+                        mbar_wait(BAR(B_RAW_FULL + rslot), (raw_it / p.n_raw) & 1u);
+                        raw = reinterpret_cast<const float*>(sRaw + (size_t)rslot * p.raw_bytes);
+                    }
+                    // destination of (plane pl, this chunk, entry e): hi at A + ((pl*4 + h) * plane_px + e) * 16, lo two planes further
+#pragma unroll
+                    for (int i = 0; i < MAXI; ++i) {
+                        if (i < n_it && it_e[i] < p.n_entries) {
+                            const int e = it_e[i];
+                            if (GEO == G_S1K3 || GEO == G_S1K1 || GEO == G_S2K1) {
+                                float v[8];
+                                if (kind == CK_TMA) {
+                                    const float* r = raw + (ch.cls ? ro1[i] : ro0[i]);
+                                    const int cp = ch.cls ? cp1 : cp0;
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) v[c] = r[c * cp];
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                                }
+                                uint8_t* d = A + ((size_t)h * p.plane_px + e) * 16;
+                                store_split8(d, d + 2 * plane_b, v);
+                            } else {  // G_S2K3: four parity planes
+                                const int y0 = 2 * (tc.oy0 - 1 + it_ei[i]), x0 = 2 * (tc.ox0 - 1 + it_ej[i]);
+                                if (kind == CK_TMA) {
+                                    const float* r = raw + ro0[i];
+                                    float2 va[8], vb[8];
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) {
+                                        va[c] = *reinterpret_cast<const float2*>(r + c * cp0);
+                                        vb[c] = *reinterpret_cast<const float2*>(r + c * cp0 + p.BW[0]);
+                                    }
+                                    float v[8];
+#pragma unroll
+                                    for (int pl = 0; pl < 4; ++pl) {
+#pragma unroll
+                                        for (int c = 0; c < 8; ++c) v[c] = pl == 0 ? va[c].x : (pl == 1 ? va[c].y : (pl == 2 ? vb[c].x : vb[c].y));
+                                        if (pl == 0 && ch.zacc) {
+                                            float a = zacc[i];
+#pragma unroll
+                                            for (int c = 0; c < 8; ++c) a = fmaf(s_wz[ch.c0 + c], v[c], a);
+                                            zacc[i] = a;
+                                        }
+                                        uint8_t* d = A + ((size_t)(pl * 4 + h) * p.plane_px + e) * 16;
+                                        store_split8(d, d + 2 * plane_b, v);
+                                    }
+                                } else if (kind == CK_COORDS) {
+#pragma unroll
+                                    for (int pl = 0; pl < 4; ++pl) {
+                                        const int y = y0 + (pl >> 1), x = x0 + (pl & 1);
+                                        const bool in = (unsigned)y < (unsigned)p.Hin && (unsigned)x < (unsigned)p.Win;
+                                        float v[8];
+#pragma unroll
+                                        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                                        if (in) {
+#pragma unroll
+                                            for (int c = 0; c < 3; ++c) v[c] = fmaf(kv[3 * c], (float)x, fmaf(kv[3 * c + 1], (float)y, kv[3 * c + 2]));
+                                        }
+                                        uint8_t* d = A + ((size_t)(pl * 4 + h) * p.plane_px + e) * 16;
+                                        store_split8(d, d + 2 * plane_b, v);
+                                    }
+                                } else {  // plane 0 only: CK_TMA_P0, CK_XYZ, CK_XYZ_T, CK_NONE (zeros)
+                                    float v[8];
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                                    if (kind == CK_TMA_P0) {
+                                        const float* r = raw + ro0[i];
+#pragma unroll
+                                        for (int c = 0; c < 8; ++c) v[c] = r[c * cp0];
+                                    } else if (kind == CK_XYZ || kind == CK_XYZ_T) {
+                                        const float z = leaky(zacc[i], p.slope);
+                                        const bool in = (unsigned)y0 < (unsigned)p.Hin && (unsigned)x0 < (unsigned)p.Win;
+                                        if (kind == CK_XYZ) {
+                                            if (in) {
+#pragma unroll
+                                                for (int c = 0; c < 3; ++c)
+                                                    v[c] = fmaf(kv[3 * c], (float)x0, fmaf(kv[3 * c + 1], (float)y0, kv[3 * c + 2])) * z;
+                                            }
+                                        } else {
+                                            const float* r = raw + ro0[i];
+#pragma unroll
+                                            for (int c = 0; c < 3; ++c) v[c] = r[c * cp0] * z;
+                                        }
+                                    }
+                                    uint8_t* d = A + ((size_t)h * p.plane_px + e) * 16;
+                                    store_split8(d, d + 2 * plane_b, v);
+                                    if (kind == CK_NONE) {  // a zero chunk is read by every tap of the stage: clear all planes
+                                        const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                                        for (int pl = 1; pl < 4; ++pl) {
+                                            uint8_t* dz = A + ((size_t)(pl * 4 + h) * p.plane_px + e) * 16;
+                                            *reinterpret_cast<uint4*>(dz) = zz;
+                                            *reinterpret_cast<uint4*>(dz + 2 * plane_b) = zz;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (is_tma) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(B_RAW_EMPTY + rslot));
+                        ++raw_it;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_A_FULL + aslot));
+                ++a_it;
+            }
+        }
+    } else if (warp == 8) {
+        // =================================================================================================================
+        // activation TMA producer (one thread)
+        // =================================================================================================================
+        if (lane == 0) {
+            uint32_t raw_it = 0;
+            const uint32_t bytes0 = (uint32_t)(p.BW[0] * p.BH[0] * 32), bytes1 = (uint32_t)(p.BW[1] * p.BH[1] * 32);
+            for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
+                const TileCoord tc = decode_tile(p, tile);
+                int x0c, y0c;
+                if (GEO == G_S1K3) { x0c = tc.ox0 - 4; y0c = tc.oy0 - 1; }
+                else if (GEO == G_S1K1) { x0c = tc.ox0; y0c = tc.oy0; }
+                else if (GEO == G_S2K3) { x0c = 2 * tc.ox0 - 4; y0c = 2 * tc.oy0 - 2; }
+                else { x0c = 2 * tc.ox0; y0c = 2 * tc.oy0; }
+                const int x1c = (tc.ox0 >> 1) - 4, y1c = (tc.oy0 >> 1) - 1;  // half-resolution sources (G_S1K3 only)
+                for (int s = 0; s < p.n_stages; ++s) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const V2Chunk ch = p.stage[s].ch[h];
+                        if (ch.kind == CK_TMA || ch.kind == CK_TMA_P0 || ch.kind == CK_XYZ_T) {
+                            const int rslot = raw_it % p.n_raw;
+                            mbar_wait(BAR(B_RAW_EMPTY + rslot), ((raw_it / p.n_raw) & 1u) ^ 1u);
+                            mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
+                            tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
+                                        (int)ch.c0, tc.n, BAR(B_RAW_FULL + rslot));
+                            ++raw_it;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // =================================================================================================================
+        // weight producer (one thread): per (stage, use, tap) one slot = [chunk 0: hi rows, lo rows][chunk 1: hi rows, lo rows]
+        // =================================================================================================================
+        if (lane == 0) {
+            uint32_t w_it = 0;
+            for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
+                const int split = (int)(tile % p.n_split);
+                for (int s = 0; s < p.n_stages; ++s) {
+                    const V2Stage& st = p.stage[s];
+                    for (int u = 0; u < st.n_use; ++u) {
+                        const V2Use us = st.use[u];
+                        const V2Conv& cv = p.conv[us.conv];
+                        const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
+                        const uint32_t piece = (uint32_t)cv.Nsl * 16u;
+                        for (int t = 0; t < ntap; ++t, ++w_it) {
+                            const int ws = w_it % p.n_w;
+                            mbar_wait(BAR(B_W_EMPTY + ws), ((w_it / p.n_w) & 1u) ^ 1u);
+                            mbar_arrive_expect_tx(BAR(B_W_FULL + ws), 4u * piece);
+                            const uint8_t* tile_g = cv.wpack + (size_t)(us.wtile + t) * ((size_t)cv.Npad * 64) + (size_t)split * piece;
+                            const uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
+#pragma unroll
+                            for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+                                    bulk_g2s(dst + (uint32_t)(c * 2 + hl) * piece, tile_g + (size_t)(hl * 2 + c) * cv.Npad * 16, piece, BAR(B_W_FULL + ws));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // =================================================================================================================
+        // MMA issuer (one thread)
+        // =================================================================================================================
+        if (lane == 0) {
+            uint32_t a_it = 0, w_it = 0, t_it = 0;
+            const uint64_t adesc0 = smem_desc(0, (uint32_t)p.plane_px * 16u, 128u);
+            const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;
+            const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
+            for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
+                const uint32_t buf = t_it % p.acc_bufs;
+                mbar_wait(BAR(B_ACC_EMPTY + buf), ((t_it / p.acc_bufs) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * tile_cols;
+                for (int s = 0; s < p.n_stages; ++s, ++a_it) {
+                    const V2Stage& st = p.stage[s];
+                    const int aslot = a_it % p.n_a;
+                    mbar_wait(BAR(B_A_FULL + aslot), (a_it / p.n_a) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(sA + (size_t)aslot * p.a_bytes);
+                    for (int u = 0; u < st.n_use; ++u) {
+                        const V2Use us = st.use[u];
+                        const V2Conv& cv = p.conv[us.conv];
+                        const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
+                        const uint32_t nsl = (uint32_t)cv.Nsl;
+                        const uint64_t bdesc0 = smem_desc(0, 2u * nsl * 16u, 128u);
+                        const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
+                        for (int t = 0; t < ntap; ++t, ++w_it) {
+                            const int ws = w_it % p.n_w;
+                            mbar_wait(BAR(B_W_FULL + ws), (w_it / p.n_w) & 1u);
+                            tc_fence_after();
+                            int pl = 0, shift = 0;
+                            if (GEO == G_S1K3) {
+                                shift = us.taps == TAPS_ALL ? (t / 3) * p.P + (t % 3) : p.P + 1;
+                            } else if (GEO == G_S2K3) {
+                                if (us.taps == TAPS_ALL) {
+                                    const int dy = t / 3 - 1, dx = t % 3 - 1;
+                                    pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
+                                    shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
+                                } else {
+                                    shift = p.P + 1;
+                                }
+                            }
+                            const uint32_t a_hi = (a_base + (uint32_t)(pl * 4 * p.plane_px + shift) * 16u) >> 4;
+                            const uint32_t w_hi = smem_u32(sW + (size_t)ws * p.w_bytes) >> 4;
+                            const uint64_t bd_hi = bdesc0 + (uint64_t)w_hi, bd_lo = bd_hi + (uint64_t)nsl;
+                            const uint32_t accum = (us.first && t == 0) ? 0u : 1u;
+                            for (int mb = 0; mb < p.MB; ++mb) {
+                                const uint64_t ad_hi = adesc0 + (uint64_t)(a_hi + (uint32_t)mb * 128u);
+                                const uint64_t ad_lo = ad_hi + a_lo_off;
+                                const uint32_t d = acc + (uint32_t)(mb * p.cols_block + cv.col);
+                                if (p.dual) {
+                                    mma_bf16_ss(d, ad_hi, bd_hi, idesc2, accum);  // [a_hi*b_hi | a_hi*b_lo]
+                                    mma_bf16_ss(d, ad_lo, bd_hi, idesc1, 1u);     //  + a_lo*b_hi
+                                } else {
+                                    mma_bf16_ss(d, ad_hi, bd_hi, idesc1, accum);
+                                    mma_bf16_ss(d, ad_lo, bd_hi, idesc1, 1u);
+                                    mma_bf16_ss(d, ad_hi, bd_lo, idesc1, 1u);
+                                }
+                            }
+                            mma_commit(BAR(B_W_EMPTY + ws));
+                        }
+                    }
+                    mma_commit(BAR(B_A_EMPTY + aslot));
+                }
+                mma_commit(BAR(B_ACC_FULL + buf));
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 12) {
+        // =================================================================================================================
+        // epilogue: TMEM -> registers -> activation -> NCHW
+        // =================================================================================================================
+        const int quarter = warp & 3;
+        const size_t oplane = (size_t)p.Hout * p.Wout;
+        const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
+        uint32_t t_it = 0;
+        for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
+            const TileCoord tc = decode_tile(p, tile);
+            const uint32_t buf = t_it % p.acc_bufs;
+            mbar_wait(BAR(B_ACC_FULL + buf), (t_it / p.acc_bufs) & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * tile_cols + ((uint32_t)(quarter * 32) << 16);
+            for (int mb = 0; mb < p.MB; ++mb) {
+                const int q = mb * 128 + quarter * 32 + lane;
+                const int oyl = q / p.P, oxl = q - oyl * p.P;
+                const int oy = tc.oy0 + oyl, ox = tc.ox0 + oxl;
+                const bool valid = oyl < p.R && oxl < p.TW && oy < p.Hout && ox < p.Wout;
+                const size_t pix = (size_t)oy * p.Wout + ox;
+                for (int j = 0; j < p.n_convs; ++j) {
+                    const V2Conv& cv = p.conv[j];
+                    const int f0 = tc.split * cv.Nsl;
+                    float* dst = cv.out + (size_t)tc.n * cv.out_stride_n + pix;
+                    const uint32_t tcol = acc + (uint32_t)(mb * p.cols_block + cv.col);
+                    for (int c = 0; c < cv.Nsl; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld_x16(tcol + (uint32_t)c, r);
+                        if (p.dual) {
+                            uint32_t r2[16];
+                            tmem_ld_x16(tcol + (uint32_t)(cv.Nsl + c), r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+                        } else {
+                            tmem_ld_wait();
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                const int f = f0 + c + k;
+                                if (f < cv.F) {
+                                    float o = __uint_as_float(r[k]);
+                                    if (cv.act) o = leaky(o, p.slope);
+                                    dst[(size_t)f * oplane] = o;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 10) tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+inline int roundup(int a, int b) { return (a + b - 1) / b * b; }
+
+// an NCHW fp32 source a 4-D tiled tensor map can describe
+bool tma_ok(const ConvSrcDev& s) {
+    return s.ptr != nullptr && ((uintptr_t)s.ptr & 15) == 0 && (s.W & 3) == 0 && (s.stride_n & 3) == 0 && s.W >= 4;
+}
+
+bool make_map4(CUtensorMap* tm, const ConvSrcDev& s, int N, int bw, int bh) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || bw > 256 || bh > 256 || bw < 1 || bh < 1) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.C, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)s.W * 4, (cuuint64_t)s.W * s.H * 4, (cuuint64_t)s.stride_n * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, 8, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(s.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+double mma_cycles(int N) {  // measured, profiles/r01_umma_probe.md
+    double c = N / 2.0, s = 32.0 + N / 4.0;
+    c = c > s ? c : s;
+    return c > 47.0 ? c : 47.0;
+}
+
+struct V2Plan {  // what the tile search decides
+    int R, TW, n_split, dual;
+};
+
+// Fill the geometry-dependent fields of p for a candidate (R, TW, n_split); returns the shared-memory footprint or -1.
+long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool has_up) {
+    const int geo = p.geo;
+    p.R = R; p.TW = TW; p.n_split = n_split; p.dual = dual;
+    int max_shift;
+    if (geo == G_S1K3) { p.P = TW + 2; p.n_entries = (R + 2) * p.P; max_shift = 2 * p.P + 2; p.BW[0] = roundup(p.P + 3, 4); p.BH[0] = R + 2; }
+    else if (geo == G_S1K1) { p.P = TW; p.n_entries = R * p.P; max_shift = 0; p.BW[0] = TW; p.BH[0] = R; }
+    else if (geo == G_S2K3) { p.P = TW + 1; p.n_entries = (R + 1) * p.P; max_shift = p.P + 1; p.BW[0] = roundup(2 * p.P + 2, 4); p.BH[0] = 2 * R + 2; }
+    else { p.P = TW; p.n_entries = R * p.P; max_shift = 0; p.BW[0] = 2 * TW; p.BH[0] = 2 * R; }
+    p.BW[1] = p.BH[1] = 4;
+    if (has_up) { p.BW[1] = roundup(TW / 2 + 5, 4); p.BH[1] = R / 2 + 2; }
+    p.n_planes = geo == G_S2K3 ? 4 : 1;
+    p.MB = cdiv(R * p.P, 128);
+    const int max_entries = (geo == G_S2K3 || geo == G_S2K1) ? 2 * V2_CONV_THREADS : 4 * V2_CONV_THREADS;
+    if (p.n_entries > max_entries || p.BW[0] > 256 || p.BH[0] > 256 || p.BW[1] > 256 || p.BH[1] > 256) return -1;
+    p.plane_px = roundup(p.n_entries > max_shift + p.MB * 128 ? p.n_entries : max_shift + p.MB * 128, 8);
+    int cols = 0, max_nsl = 0;
+    for (int j = 0; j < p.n_convs; ++j) {
+        V2Conv& cv = p.conv[j];
+        if (cv.Npad % (16 * n_split)) return -1;
+        cv.Nsl = cv.Npad / n_split;
+        if (cv.Nsl > 256 || (dual && cv.Nsl > 128)) return -1;
+        cv.col = cols;
+        cols += (dual ? 2 : 1) * cv.Nsl;
+        max_nsl = cv.Nsl > max_nsl ? cv.Nsl : max_nsl;
+    }
+    p.cols_block = cols;
+    if (p.MB * cols > 512) return -1;
+    p.acc_bufs = 2 * p.MB * cols <= 512 ? 2 : 1;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.acc_bufs * p.MB * cols) p.tmem_cols <<= 1;
+    const int raw0 = p.BW[0] * p.BH[0] * 32, raw1 = has_up ? p.BW[1] * p.BH[1] * 32 : 0;
+    p.raw_bytes = roundup(raw0 > raw1 ? raw0 : raw1, 128);
+    p.a_bytes = roundup(p.n_planes * 4 * p.plane_px * 16, 128);
+    p.w_bytes = roundup(max_nsl * 64, 128);
+    p.tiles_x = cdiv(p.Wout, TW);
+    p.tiles_y = cdiv(p.Hout, R);
+    p.n_tiles = (long long)p.N * p.tiles_x * p.tiles_y * n_split;
+    // minimum rings: 2 raw, 2 A, 2 W
+    return (long long)V2_HEADER + 2LL * p.raw_bytes + 2LL * p.a_bytes + 2LL * p.w_bytes;
+}
+
+// Memo of the tile search (a pure function of the program shape); guarded by a mutex, so concurrent callers are fine.
+struct PlanKey {
+    int v[24];
+    bool operator==(const PlanKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct PlanEntry {
+    PlanKey key;
+    V2Plan plan;
+};
+std::mutex g_plan_mutex;
+std::vector<PlanEntry> g_plans;
+
+V2Plan search_plan(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunks, int sms) {
+    const int geo = p.geo;
+    double best = 1e300;
+    V2Plan plan = {0, 0, 0, 0};
+    V2Params trial = p;
+    const int tw_step = geo == G_S1K3 ? (has_up ? 8 : 4) : (geo == G_S1K1 ? 4 : 2);
+    const int r_step = (geo == G_S1K3 && has_up) ? 2 : 1;
+    for (int n_split = 1; n_split <= 8; n_split *= 2) {
+        for (int dual = 1; dual >= 0; --dual) {
+            // per-M-block MMA cycles and per-tile weight bytes of this (n_split, dual)
+            double mma_mb = 0, wbytes = 0;
+            bool ok = true;
+            for (int j = 0; j < p.n_convs; ++j)
+                if (p.conv[j].Npad % (16 * n_split) || p.conv[j].Npad / n_split > (dual ? 128 : 256)) ok = false;
+            if (!ok) continue;
+            for (int s = 0; s < p.n_stages; ++s)
+                for (int u = 0; u < p.stage[s].n_use; ++u) {
+                    const V2Use& us = p.stage[s].use[u];
+                    const int nsl = p.conv[us.conv].Npad / n_split;
+                    const int nt = us.taps == TAPS_ALL ? p.conv[us.conv].ntaps : 1;
+                    mma_mb += nt * (dual ? mma_cycles(2 * nsl) + mma_cycles(nsl) : 3.0 * mma_cycles(nsl));
+                    wbytes += (double)nt * nsl * 64.0;
+                }
+            int last_tw = -1;
+            for (int parts = 1; parts <= 64; ++parts) {
+                int TW = roundup(cdiv(p.Wout, parts), tw_step);
+                if (TW > 248) continue;
+                if (TW == last_tw) continue;
+                last_tw = TW;
+                for (int R = r_step; R <= 64; R += r_step) {
+                    if (R - r_step >= p.Hout) break;
+                    const long long smem_min = apply_geometry(trial, R, TW, n_split, dual, has_up);
+                    if (smem_min < 0 || smem_min > V2_SMEM_LIMIT) continue;
+                    const double mma = mma_mb * trial.MB;
+                    const double items = (double)cdiv(trial.n_entries, V2_CONV_THREADS);
+                    const double cvt = (double)n_chunks * items * (trial.n_planes * 45.0 + 10.0) * V2_CONV_WARPS / 2.0 + p.n_stages * 150.0;
+                    double outb = 0;
+                    for (int j = 0; j < p.n_convs; ++j) outb += (double)trial.conv[j].Nsl * R * TW * 4.0;
+                    const double mem = ((double)n_tma_chunks * trial.raw_bytes + wbytes + outb) / 24.0;  // ~ one SM's share of HBM/L2, B/clk
+                    const double epi = (double)trial.MB * trial.cols_block * 10.0;                       // tcgen05.ld + stores of 4 warps
+                    double tile = mma > cvt ? mma : cvt;
+                    tile = tile > mem ? tile : mem;
+                    tile = tile > epi ? tile : epi;
+                    if (trial.acc_bufs == 1) tile += epi;
+                    const double waves = (double)cdiv((int)(trial.n_tiles > (1 << 30) ? (1 << 30) : trial.n_tiles), sms);
+                    const double total = waves * tile + tile + 4000.0;  // + pipeline fill
+                    if (total < best) { best = total; plan = {R, TW, n_split, dual}; }
+                }
+            }
+        }
+    }
+    return plan;
+}
+
+int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, cudaStream_t stream) {
+    const int geo = p.geo;
+    int n_ops = 0, n_tma_chunks = 0, n_chunks = 0;  // per tile
+    for (int s = 0; s < p.n_stages; ++s) {
+        for (int h = 0; h < 2; ++h) {
+            const int k = p.stage[s].ch[h].kind;
+            n_chunks += 1;
+            if (k == CK_TMA || k == CK_TMA_P0 || k == CK_XYZ_T) ++n_tma_chunks;
+        }
+        for (int u = 0; u < p.stage[s].n_use; ++u) n_ops += p.stage[s].use[u].taps == TAPS_ALL ? p.conv[p.stage[s].use[u].conv].ntaps : 1;
+    }
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        }
+    }
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    {
+        int* k = key.v;
+        k[0] = geo; k[1] = p.N; k[2] = p.Hin; k[3] = p.Win; k[4] = p.Hout; k[5] = p.Wout; k[6] = p.n_stages; k[7] = p.n_convs;
+        for (int j = 0; j < p.n_convs; ++j) { k[8 + 2 * j] = p.conv[j].Npad; k[9 + 2 * j] = p.conv[j].ntaps; }
+        k[14] = has_up; k[15] = n_chunks; k[16] = n_tma_chunks; k[17] = n_ops; k[18] = sms;
+    }
+    V2Plan plan = {0, 0, 0, 0};
+    bool found = false;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        for (const PlanEntry& e : g_plans)
+            if (e.key == key) { plan = e.plan; found = true; break; }
+    }
+    if (!found) {
+        plan = search_plan(p, has_up, n_chunks, n_tma_chunks, sms);
+        if (const char* ov = getenv("KBNET_V2_PLAN")) {  // debugging aid: "R,TW,n_split,dual"
+            int a, b, c, d;
+            if (sscanf(ov, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) plan = {a, b, c, d};
+        }
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        if (g_plans.size() < 4096) g_plans.push_back({key, plan});
+    }
+    KB_CHECK_ARG(plan.R > 0, "conv(v2): no tile fits");
+    long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
+    p.n_raw = 2; p.n_a = 2; p.n_w = 2;
+    // spend the remaining shared memory: weights slots first (cheap), then raw slots, then a third A slot
+    while (p.n_w < V2_MAX_W && p.n_w < 4 && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
+    while (p.n_raw < 4 && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
+    if (p.n_stages > 2 && used + p.a_bytes <= V2_SMEM_LIMIT) { ++p.n_a; used += p.a_bytes; }
+    while (p.n_w < V2_MAX_W && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
+    while (p.n_raw < V2_MAX_RAW && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
+    if (used < 120 * 1024) used = 120 * 1024;  // one CTA per SM (the TMEM budget assumes it)
+
+    V2Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int i = 0; i < n_maps; ++i)
+        KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]]), "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
+
+    const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
+    KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
+    static const bool debug = getenv("KBNET_V2_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "[conv v2] geo %d  %dx%dx%d -> %dx%d  stages %d convs %d Npad %d/%d/%d | R %d TW %d P %d MB %d split %d dual %d | tiles %lld grid %lld | "
+                "raw %d x %d B, A %d x %d B, W %d x %d B, smem %lld | tmem %d cols x %d bufs\n",
+                geo, p.N, p.Hin, p.Win, p.Hout, p.Wout, p.n_stages, p.n_convs, p.conv[0].Npad, p.conv[1].Npad, p.conv[2].Npad, p.R, p.TW, p.P, p.MB,
+                p.n_split, p.dual, p.n_tiles, grid, p.n_raw, p.raw_bytes, p.n_a, p.a_bytes, p.n_w, p.w_bytes, used, p.MB * p.cols_block, p.acc_bufs);
+#define V2_LAUNCH(G)                                                                                                  \
+    do {                                                                                                              \
+        KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));     \
+        conv_v2_kernel<G><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                             \
+    } while (0)
+    if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
+    else if (geo == G_S1K1) V2_LAUNCH(G_S1K1);
+    else if (geo == G_S2K3) V2_LAUNCH(G_S2K3);
+    else V2_LAUNCH(G_S2K1);
+#undef V2_LAUNCH
+    KB_CUDA(cudaGetLastError());
+    count_launch();
+    count_launch_v2();
+    return 0;
+}
+
+// same grouping as conv_umma.cu / conv_pack_weights: every source is cut into chunks of <= 8 channels, padded to an even count
+int chunk_list(const int* src_channels, int n_src, int* src_of, int* c0_of, int* nch_of) {
+    int g = 0;
+    for (int s = 0; s < n_src; ++s)
+        for (int c0 = 0; c0 < src_channels[s]; c0 += 8) {
+            if (g >= 2 * V2_MAX_STAGES) return -1;
+            src_of[g] = s; c0_of[g] = c0; nch_of[g] = src_channels[s] - c0 < 8 ? src_channels[s] - c0 : 8;
+            ++g;
+        }
+    if (g & 1) {
+        if (g >= 2 * V2_MAX_STAGES) return -1;
+        src_of[g] = -1; c0_of[g] = 0; nch_of[g] = 0;
+        ++g;
+    }
+    return g;
+}
+
+bool v2_disabled() {
+    static const bool off = getenv("KBNET_CONV_V1") != nullptr;
+    return off;
+}
+
+}  // namespace
+
+// ---- plain convolution ------------------------------------------------------------------------------------------------
+bool conv_v2_supported(const ConvParams& c) {
+    if (v2_disabled()) return false;
+    if (!((c.ksize == 3 || c.ksize == 1) && (c.stride == 1 || c.stride == 2))) return false;
+    if (c.n_src < 1 || c.n_src > V2_MAX_MAPS) return false;
+    const int Npad = (c.F + 15) & ~15;
+    if (Npad > 1024) return false;
+    for (int i = 0; i < c.n_src; ++i) {
+        const ConvSrcDev& s = c.src[i];
+        if (!tma_ok(s)) return false;
+        if (s.mode == SRC_DIRECT) continue;
+        if (s.mode == SRC_UPSAMPLE && c.ksize == 3 && c.stride == 1 && c.Hin == 2 * s.H && c.Win == 2 * s.W) continue;
+        return false;
+    }
+    int chans[CONV_MAX_SRC], so[2 * V2_MAX_STAGES], co[2 * V2_MAX_STAGES], no[2 * V2_MAX_STAGES];
+    for (int i = 0; i < c.n_src; ++i) chans[i] = c.src[i].C;
+    return chunk_list(chans, c.n_src, so, co, no) > 0;
+}
+
+int conv_v2_launch(const ConvParams& c, const void* wpack, cudaStream_t stream) {
+    KB_CHECK_ARG(wpack && ((uintptr_t)wpack & 15) == 0, "conv(v2): packed weights missing or misaligned");
+    static thread_local V2Params q;  // large: keep it off the stack
+    memset(&q, 0, sizeof(q));
+    q.geo = c.stride == 1 ? (c.ksize == 3 ? G_S1K3 : G_S1K1) : (c.ksize == 3 ? G_S2K3 : G_S2K1);
+    q.N = c.N; q.Hin = c.Hin; q.Win = c.Win; q.Hout = c.Hout; q.Wout = c.Wout;
+    q.slope = c.slope;
+    q.n_convs = 1;
+    V2Conv& cv = q.conv[0];
+    cv.wpack = (const uint8_t*)wpack; cv.out = c.out; cv.out_stride_n = c.out_stride_n;
+    cv.F = c.F; cv.Npad = (c.F + 15) & ~15; cv.act = c.act; cv.ntaps = c.ksize * c.ksize;
+    int chans[CONV_MAX_SRC], so[2 * V2_MAX_STAGES], co[2 * V2_MAX_STAGES], no[2 * V2_MAX_STAGES];
+    for (int i = 0; i < c.n_src; ++i) chans[i] = c.src[i].C;
+    const int ng = chunk_list(chans, c.n_src, so, co, no);
+    KB_CHECK_ARG(ng > 0, "conv(v2): too many input channels");
+    q.n_stages = ng / 2;
+    bool has_up = false;
+    uint8_t map_cls[V2_MAX_MAPS] = {0, 0, 0, 0};
+    for (int i = 0; i < c.n_src; ++i) { map_cls[i] = c.src[i].mode == SRC_UPSAMPLE ? 1 : 0; has_up = has_up || map_cls[i]; }
+    for (int s = 0; s < q.n_stages; ++s) {
+        V2Stage& st = q.stage[s];
+        for (int h = 0; h < 2; ++h) {
+            const int g = 2 * s + h;
+            V2Chunk& ch = st.ch[h];
+            if (so[g] < 0) { ch.kind = CK_NONE; continue; }
+            ch.kind = CK_TMA; ch.tmap = (uint8_t)so[g]; ch.nch = (uint8_t)no[g]; ch.c0 = (uint16_t)co[g]; ch.cls = map_cls[so[g]];
+        }
+        st.n_use = 1;
+        st.use[0].conv = 0; st.use[0].taps = TAPS_ALL; st.use[0].first = s == 0; st.use[0].wtile = (uint32_t)(s * cv.ntaps);
+    }
+    return v2_launch(q, c.src, c.n_src, map_cls, has_up, stream);
+}
+
+// ---- the fused Calibrated Backprojection block ----------------------------------------------------------------------------
+// One launch for reference src/net_utils.py:1343-1371.  `coordinates` (the [N,3,H,W] tensor the reference passes) or `kinv`.
+bool kb_fused_supported(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
+                        const float* coordinates, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f) {
+    if (v2_disabled()) return false;
+    if ((C_i & 15) || (C_d & 15) || (C_f & 7) || C_d > V2_MAX_ZC) return false;
+    if ((W & 3) || W < 4) return false;
+    auto okp = [](const float* p, long long sn) { return ((uintptr_t)p & 15) == 0 && (sn & 3) == 0; };
+    if (!okp(image, image_sn) || !okp(depth, depth_sn) || (fused && !okp(fused, fused_sn)) || (coordinates && !okp(coordinates, 0))) return false;
+    const int np_i = (F_i + 15) & ~15, np_d = (F_d + 15) & ~15, np_f = (F_f + 15) & ~15;
+    // some power-of-two filter split must bring the three accumulators under 512 TMEM columns
+    for (int ns = 1; ns <= 8; ns *= 2)
+        if (np_i % (16 * ns) == 0 && np_d % (16 * ns) == 0 && np_f % (16 * ns) == 0 && (np_i + np_d + np_f) / ns <= 512 && np_i / ns <= 256 &&
+            np_f / ns <= 256)
+            return C_i / 16 + C_d / 16 + 1 + (C_f / 8 + 2) / 2 <= V2_MAX_STAGES;
+    return false;
+}
+
+int kb_fused_launch(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
+                    const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_proj,
+                    const void* wpack_image, int F_i, const void* wpack_depth, int F_d, const void* wpack_fused, int F_f, float slope,
+                    float* out_image, long long out_image_sn, float* out_depth, long long out_depth_sn, float* out_fused, long long out_fused_sn,
+                    cudaStream_t stream) {
+    static thread_local V2Params q;
+    memset(&q, 0, sizeof(q));
+    q.geo = G_S2K3;
+    q.N = N; q.Hin = H; q.Win = W; q.Hout = (H - 1) / 2 + 1; q.Wout = (W - 1) / 2 + 1;
+    q.slope = slope; q.kinv = kinv; q.w_proj = w_proj; q.C_z = C_d;
+    q.n_convs = 3;
+    const void* packs[3] = {wpack_image, wpack_depth, wpack_fused};
+    float* outs[3] = {out_image, out_depth, out_fused};
+    const long long osn[3] = {out_image_sn, out_depth_sn, out_fused_sn};
+    const int Fs[3] = {F_i, F_d, F_f};
+    for (int j = 0; j < 3; ++j) {
+        V2Conv& cv = q.conv[j];
+        cv.wpack = (const uint8_t*)packs[j]; cv.out = outs[j]; cv.out_stride_n = osn[j];
+        cv.F = Fs[j]; cv.Npad = (Fs[j] + 15) & ~15; cv.act = 1; cv.ntaps = j == 2 ? 1 : 9;
+    }
+    // tensor maps: 0 image, 1 depth, 2 fused, 3 coordinates
+    ConvSrcDev srcs[V2_MAX_MAPS];
+    memset(srcs, 0, sizeof(srcs));
+    auto mk = [&](const float* ptr, int C, long long sn) {
+        ConvSrcDev s;
+        memset(&s, 0, sizeof(s));
+        s.ptr = ptr; s.C = C; s.H = H; s.W = W; s.stride_n = sn;
+        return s;
+    };
+    srcs[0] = mk(image, C_i, image_sn);
+    srcs[1] = mk(depth, C_d, depth_sn);
+    srcs[2] = fused ? mk(fused, C_f, fused_sn) : srcs[0];
+    srcs[3] = coordinates ? mk(coordinates, 3, 3LL * H * W) : srcs[0];
+    const uint8_t map_cls[V2_MAX_MAPS] = {0, 0, 0, 0};
+    int s = 0;
+    // (1) depth chunks -> conv_depth (9 taps) and the z projection
+    for (int j = 0; j < C_d / 16; ++j, ++s) {
+        V2Stage& st = q.stage[s];
+        for (int h = 0; h < 2; ++h) { st.ch[h].kind = CK_TMA; st.ch[h].tmap = 1; st.ch[h].nch = 8; st.ch[h].c0 = (uint16_t)(16 * j + 8 * h); st.ch[h].zacc = 1; }
+        st.n_use = 1;
+        st.use[0].conv = 1; st.use[0].taps = TAPS_ALL; st.use[0].first = j == 0; st.use[0].wtile = (uint32_t)(j * 9);
+    }
+    // (2) camera coordinates (3 channels + a zero chunk) -> conv_depth
+    {
+        V2Stage& st = q.stage[s];
+        if (coordinates) { st.ch[0].kind = CK_TMA; st.ch[0].tmap = 3; st.ch[0].nch = 3; st.ch[0].c0 = 0; }
+        else st.ch[0].kind = CK_COORDS;
+        st.ch[1].kind = CK_NONE;
+        st.n_use = 1;
+        st.use[0].conv = 1; st.use[0].taps = TAPS_ALL; st.use[0].first = 0; st.use[0].wtile = (uint32_t)((C_d / 16) * 9);
+        ++s;
+    }
+    // (3) image chunks -> conv_image (9 taps) and conv_fused (centre tap)
+    for (int j = 0; j < C_i / 16; ++j, ++s) {
+        V2Stage& st = q.stage[s];
+        for (int h = 0; h < 2; ++h) { st.ch[h].kind = CK_TMA; st.ch[h].tmap = 0; st.ch[h].nch = 8; st.ch[h].c0 = (uint16_t)(16 * j + 8 * h); }
+        st.n_use = 2;
+        st.use[0].conv = 0; st.use[0].taps = TAPS_ALL; st.use[0].first = j == 0; st.use[0].wtile = (uint32_t)(j * 9);
+        st.use[1].conv = 2; st.use[1].taps = TAPS_CENTER; st.use[1].first = j == 0; st.use[1].wtile = (uint32_t)j;
+    }
+    // (4) xyz = coordinates * z, then the incoming fused features -> conv_fused (even pixels only)
+    {
+        const int n_rest = 1 + C_f / 8;  // chunks of conv_fused after the image: xyz, fused...
+        for (int g = 0; g < n_rest + (n_rest & 1); g += 2, ++s) {
+            V2Stage& st = q.stage[s];
+            for (int h = 0; h < 2; ++h) {
+                const int k = g + h;
+                V2Chunk& ch = st.ch[h];
+                if (k == 0) {
+                    if (coordinates) { ch.kind = CK_XYZ_T; ch.tmap = 3; ch.nch = 3; ch.c0 = 0; }
+                    else ch.kind = CK_XYZ;
+                } else if (k < n_rest) {
+                    ch.kind = CK_TMA_P0; ch.tmap = 2; ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1));
+                } else {
+                    ch.kind = CK_NONE;
+                }
+            }
+            st.n_use = 1;
+            st.use[0].conv = 2; st.use[0].taps = TAPS_CENTER; st.use[0].first = 0; st.use[0].wtile = (uint32_t)(C_i / 16 + g / 2);
+        }
+    }
+    KB_CHECK_ARG(s <= V2_MAX_STAGES, "kb(v2): too many stages");
+    q.n_stages = s;
+    return v2_launch(q, srcs, V2_MAX_MAPS, map_cls, false, stream);
+}
+
+}  // namespace kbnet

@@ -36,6 +36,8 @@ int         kbnet_version(void);
 const char* kbnet_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (statistics only; monotonically increasing). */
 unsigned long long kbnet_launch_count(void);
+/* ... of which launches of the persistent TMA-fed tcgen05 engine (plain convolutions and fused KB blocks). */
+unsigned long long kbnet_tma_engine_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * SparseToDensePool.forward -- replaces reference src/networks.py:2168-2196 (module ctor :2100-2166).
