@@ -117,6 +117,18 @@ __device__ __forceinline__ void store_split8(uint8_t* hi_dst, uint8_t* lo_dst, c
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(a.y, b.y, c.y, d.y);
 }
 
+// exactly one lane of the (converged) warp gets true; lets the compiler keep warp-uniform operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
 struct TileCoord {
     int n, oy0, ox0, split;
 };
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         // =================================================================================================================
         // activation TMA producer (one thread)
         // =================================================================================================================
-        if (lane == 0) {
+        {
             uint32_t raw_it = 0;
             const uint32_t bytes0 = (uint32_t)(p.BW[0] * p.BH[0] * 32), bytes1 = (uint32_t)(p.BW[1] * p.BH[1] * 32);
             for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
@@ -342,9 +354,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                         if (ch.kind == CK_TMA || ch.kind == CK_TMA_P0 || ch.kind == CK_XYZ_T) {
                             const int rslot = raw_it % p.n_raw;
                             mbar_wait(BAR(B_RAW_EMPTY + rslot), ((raw_it / p.n_raw) & 1u) ^ 1u);
-                            mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
-                            tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
-                                        (int)ch.c0, tc.n, BAR(B_RAW_FULL + rslot));
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
+                                tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
+                                            (int)ch.c0, tc.n, BAR(B_RAW_FULL + rslot));
+                            }
+                            __syncwarp();
                             ++raw_it;
                         }
                     }
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         // =================================================================================================================
         // weight producer (one thread): per (stage, use, tap) one slot = [chunk 0: hi rows, lo rows][chunk 1: hi rows, lo rows]
         // =================================================================================================================
-        if (lane == 0) {
+        {
             uint32_t w_it = 0;
             for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
                 const int split = (int)(tile % p.n_split);
@@ -370,14 +385,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                         for (int t = 0; t < ntap; ++t, ++w_it) {
                             const int ws = w_it % p.n_w;
                             mbar_wait(BAR(B_W_EMPTY + ws), ((w_it / p.n_w) & 1u) ^ 1u);
-                            mbar_arrive_expect_tx(BAR(B_W_FULL + ws), 4u * piece);
                             const uint8_t* tile_g = cv.wpack + (size_t)(us.wtile + t) * ((size_t)cv.Npad * 64) + (size_t)split * piece;
                             const uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(BAR(B_W_FULL + ws), 4u * piece);
 #pragma unroll
-                            for (int hl = 0; hl < 2; ++hl)
+                                for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
-                                for (int c = 0; c < 2; ++c)
-                                    bulk_g2s(dst + (uint32_t)(c * 2 + hl) * piece, tile_g + (size_t)(hl * 2 + c) * cv.Npad * 16, piece, BAR(B_W_FULL + ws));
+                                    for (int c = 0; c < 2; ++c)
+                                        bulk_g2s(dst + (uint32_t)(c * 2 + hl) * piece, tile_g + (size_t)(hl * 2 + c) * cv.Npad * 16, piece, BAR(B_W_FULL + ws));
+                            }
+                            __syncwarp();
                         }
                     }
                 }
@@ -386,73 +404,78 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 10) {
         // =================================================================================================================
-        // MMA issuer (one thread)
+        // MMA issuer.  The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
+        // one elected lane issues (tcgen05.mma / commit are single-thread instructions).
         // =================================================================================================================
-        if (lane == 0) {
-            uint32_t a_it = 0, w_it = 0, t_it = 0;
-            const uint64_t adesc0 = smem_desc(0, (uint32_t)p.plane_px * 16u, 128u);
-            const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;
-            const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
-            for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
-                const uint32_t buf = t_it % p.acc_bufs;
-                mbar_wait(BAR(B_ACC_EMPTY + buf), ((t_it / p.acc_bufs) & 1u) ^ 1u);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        uint32_t a_it = 0, w_it = 0, t_it = 0;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
+        const uint32_t a_lbo = (((uint32_t)p.plane_px * 16u) >> 4) << 16;          // LBO: chunk 0 -> chunk 1 plane
+        const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;          // hi planes -> lo planes
+        const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
+        const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+        for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
+            const uint32_t buf = t_it % p.acc_bufs;
+            mbar_wait(BAR(B_ACC_EMPTY + buf), ((t_it / p.acc_bufs) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_u + buf * tile_cols;
+            for (int s = 0; s < p.n_stages; ++s, ++a_it) {
+                const V2Stage& st = p.stage[s];
+                const uint32_t aslot = a_it % p.n_a;
+                mbar_wait(BAR(B_A_FULL + aslot), (a_it / p.n_a) & 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + buf * tile_cols;
-                for (int s = 0; s < p.n_stages; ++s, ++a_it) {
-                    const V2Stage& st = p.stage[s];
-                    const int aslot = a_it % p.n_a;
-                    mbar_wait(BAR(B_A_FULL + aslot), (a_it / p.n_a) & 1u);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + (size_t)aslot * p.a_bytes);
-                    for (int u = 0; u < st.n_use; ++u) {
-                        const V2Use us = st.use[u];
-                        const V2Conv& cv = p.conv[us.conv];
-                        const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
-                        const uint32_t nsl = (uint32_t)cv.Nsl;
-                        const uint64_t bdesc0 = smem_desc(0, 2u * nsl * 16u, 128u);
-                        const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
-                        for (int t = 0; t < ntap; ++t, ++w_it) {
-                            const int ws = w_it % p.n_w;
-                            mbar_wait(BAR(B_W_FULL + ws), (w_it / p.n_w) & 1u);
-                            tc_fence_after();
-                            int pl = 0, shift = 0;
-                            if (GEO == G_S1K3) {
-                                shift = us.taps == TAPS_ALL ? (t / 3) * p.P + (t % 3) : p.P + 1;
-                            } else if (GEO == G_S2K3) {
-                                if (us.taps == TAPS_ALL) {
-                                    const int dy = t / 3 - 1, dx = t % 3 - 1;
-                                    pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
-                                    shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
-                                } else {
-                                    shift = p.P + 1;
-                                }
+                const uint32_t a_base = sA_u + aslot * (uint32_t)p.a_bytes;
+                for (int u = 0; u < st.n_use; ++u) {
+                    const V2Use us = st.use[u];
+                    const V2Conv& cv = p.conv[us.conv];
+                    const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
+                    const uint32_t nsl = (uint32_t)cv.Nsl;
+                    const uint32_t b_lbo = ((2u * nsl * 16u) >> 4) << 16;
+                    const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
+                    const uint32_t dcol = acc + (uint32_t)cv.col;
+                    for (int t = 0; t < ntap; ++t, ++w_it) {
+                        const uint32_t ws = w_it % p.n_w;
+                        mbar_wait(BAR(B_W_FULL + ws), (w_it / p.n_w) & 1u);
+                        tc_fence_after();
+                        int pl = 0, shift = 0;
+                        if (GEO == G_S1K3) {
+                            shift = us.taps == TAPS_ALL ? (t / 3) * p.P + (t % 3) : p.P + 1;
+                        } else if (GEO == G_S2K3) {
+                            if (us.taps == TAPS_ALL) {
+                                const int dy = t / 3 - 1, dx = t % 3 - 1;
+                                pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
+                                shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
+                            } else {
+                                shift = p.P + 1;
                             }
-                            const uint32_t a_hi = (a_base + (uint32_t)(pl * 4 * p.plane_px + shift) * 16u) >> 4;
-                            const uint32_t w_hi = smem_u32(sW + (size_t)ws * p.w_bytes) >> 4;
-                            const uint64_t bd_hi = bdesc0 + (uint64_t)w_hi, bd_lo = bd_hi + (uint64_t)nsl;
-                            const uint32_t accum = (us.first && t == 0) ? 0u : 1u;
+                        }
+                        const uint32_t a_hi = ((a_base + (uint32_t)(pl * 4 * p.plane_px + shift) * 16u) >> 4) | a_lbo;
+                        const uint32_t b_hi = ((sW_u + ws * (uint32_t)p.w_bytes) >> 4) | b_lbo;
+                        const uint32_t accum = (us.first && t == 0) ? 0u : 1u;
+                        if (elect_one()) {
                             for (int mb = 0; mb < p.MB; ++mb) {
-                                const uint64_t ad_hi = adesc0 + (uint64_t)(a_hi + (uint32_t)mb * 128u);
-                                const uint64_t ad_lo = ad_hi + a_lo_off;
-                                const uint32_t d = acc + (uint32_t)(mb * p.cols_block + cv.col);
+                                const uint32_t a0 = a_hi + (uint32_t)mb * 128u;
+                                const uint32_t d = dcol + (uint32_t)(mb * p.cols_block);
                                 if (p.dual) {
-                                    mma_bf16_ss(d, ad_hi, bd_hi, idesc2, accum);  // [a_hi*b_hi | a_hi*b_lo]
-                                    mma_bf16_ss(d, ad_lo, bd_hi, idesc1, 1u);     //  + a_lo*b_hi
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi, desc_hi), idesc2, accum);        // [a_hi*b_hi | a_hi*b_lo]
+                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b_hi, desc_hi), idesc1, 1u);  //  + a_lo*b_hi
                                 } else {
-                                    mma_bf16_ss(d, ad_hi, bd_hi, idesc1, accum);
-                                    mma_bf16_ss(d, ad_lo, bd_hi, idesc1, 1u);
-                                    mma_bf16_ss(d, ad_hi, bd_lo, idesc1, 1u);
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi, desc_hi), idesc1, accum);
+                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b_hi, desc_hi), idesc1, 1u);
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi + nsl, desc_hi), idesc1, 1u);
                                 }
                             }
                             mma_commit(BAR(B_W_EMPTY + ws));
                         }
+                        __syncwarp();
                     }
-                    mma_commit(BAR(B_A_EMPTY + aslot));
                 }
-                mma_commit(BAR(B_ACC_FULL + buf));
+                if (elect_one()) mma_commit(BAR(B_A_EMPTY + aslot));
+                __syncwarp();
             }
+            if (elect_one()) mma_commit(BAR(B_ACC_FULL + buf));
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp >= 12) {
         // =================================================================================================================
         // epilogue: TMEM -> registers -> activation -> NCHW
