@@ -70,7 +70,7 @@ struct V2Stage {
     int n_use, pad;
 };
 struct V2Conv {
-    const uint8_t* wpack;  // [tile][hi|lo][chunk 0|1][Npad rows][16 B]   (conv_pack_weights)
+    const uint8_t* wpack;  // [tile][g = f/8][hi|lo][chunk 0|1][8 rows][16 B]   (conv_pack_weights)
     float* out;
     long long out_stride_n;
     int F, Npad, Nsl;  // Nsl = filters per split part
@@ -89,10 +89,13 @@ struct V2Params {
     int raw_bytes, a_bytes, w_bytes;  // bytes per ring slot
     int n_raw, n_a, n_w;
     int cols_block, acc_bufs, tmem_cols;
+    int T;  // taps per weight-ring slot for the 9-tap uses (1, 3 or 9); single-tap uses take one slot each
     float slope;
     const float* kinv;    // [N, 9]   (CK_COORDS / CK_XYZ)
     const float* w_proj;  // [C_z]    (zacc)
     int C_z;
+    int exp;              // experiment switches (KBNET_V2_EXP), 0 in production
+    long long* dbg;       // optional timeline buffer (KBNET_V2_TIMELINE): [role 0..4][4096] clock64 stamps of CTA 0
 };
 struct alignas(64) V2Maps {
     CUtensorMap m[V2_MAX_MAPS];
@@ -128,6 +131,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
+
+// ring position kept incrementally (a runtime modulo costs ~30 dependent instructions on the single issuing warp)
+struct Ring {
+    uint32_t slot = 0, phase = 0;
+    __device__ __forceinline__ void advance(uint32_t n) {
+        if (++slot == n) { slot = 0; phase ^= 1u; }
+    }
+};
+
+#define V2_STAMP(role, idx)                                                                             \
+    do {                                                                                                  \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 4096) p.dbg[(role) * 4096 + (idx)] = clock64(); \
+    } while (0)
 
 struct TileCoord {
     int n, oy0, ox0, split;
@@ -197,7 +213,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         }
         const int cp0 = p.BW[0] * p.BH[0], cp1 = p.BW[1] * p.BH[1];  // channel pitch of the raw tile (floats)
         const size_t plane_b = (size_t)p.plane_px * 16;
-        uint32_t raw_it = 0, a_it = 0;
+        Ring raw_r, a_r;
+        int dbg_i = 0;
+        const bool dbg_on = tid == 0;
         for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
             const TileCoord tc = decode_tile(p, tile);
             float zacc[MAXI];
@@ -210,8 +228,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             }
             for (int s = 0; s < p.n_stages; ++s) {
                 const V2Stage& st = p.stage[s];
-                const int aslot = a_it % p.n_a;
-                mbar_wait(BAR(B_A_EMPTY + aslot), ((a_it / p.n_a) & 1u) ^ 1u);
+                const int aslot = (int)a_r.slot;
+                mbar_wait(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
+                if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
                 uint8_t* A = sA + (size_t)aslot * p.a_bytes;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -221,14 +240,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     const float* raw = nullptr;
                     int rslot = 0;
                     if (is_tma) {
-                        rslot = raw_it % p.n_raw;
-                        mbar_wait(BAR(B_RAW_FULL + rslot), (raw_it / p.n_raw) & 1u);
+                        rslot = (int)raw_r.slot;
+                        mbar_wait(BAR(B_RAW_FULL + rslot), raw_r.phase);
+                        if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
                         raw = reinterpret_cast<const float*>(sRaw + (size_t)rslot * p.raw_bytes);
                     }
                     // destination of (plane pl, this chunk, entry e): hi at A + ((pl*4 + h) * plane_px + e) * 16, lo two planes further
 #pragma unroll
                     for (int i = 0; i < MAXI; ++i) {
-                        if (i < n_it && it_e[i] < p.n_entries) {
+                        if (i < n_it && it_e[i] < p.n_entries && !(p.exp & 2)) {
                             const int e = it_e[i];
                             if (GEO == G_S1K3 || GEO == G_S1K1 || GEO == G_S2K1) {
                                 float v[8];
@@ -323,21 +343,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     if (is_tma) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(BAR(B_RAW_EMPTY + rslot));
-                        ++raw_it;
+                        raw_r.advance((uint32_t)p.n_raw);
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_A_FULL + aslot));
-                ++a_it;
+                if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
+                a_r.advance((uint32_t)p.n_a);
             }
         }
     } else if (warp == 8) {
         // =================================================================================================================
         // activation TMA producer (one thread)
         // =================================================================================================================
-        {
-            uint32_t raw_it = 0;
+        if (elect_one()) {
+            Ring raw_r;
+            int dbg_i = 0;
             const uint32_t bytes0 = (uint32_t)(p.BW[0] * p.BH[0] * 32), bytes1 = (uint32_t)(p.BW[1] * p.BH[1] * 32);
             for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
                 const TileCoord tc = decode_tile(p, tile);
@@ -352,15 +374,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     for (int h = 0; h < 2; ++h) {
                         const V2Chunk ch = p.stage[s].ch[h];
                         if (ch.kind == CK_TMA || ch.kind == CK_TMA_P0 || ch.kind == CK_XYZ_T) {
-                            const int rslot = raw_it % p.n_raw;
-                            mbar_wait(BAR(B_RAW_EMPTY + rslot), ((raw_it / p.n_raw) & 1u) ^ 1u);
-                            if (elect_one()) {
-                                mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
-                                tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
-                                            (int)ch.c0, tc.n, BAR(B_RAW_FULL + rslot));
-                            }
-                            __syncwarp();
-                            ++raw_it;
+                            const int rslot = (int)raw_r.slot;
+                            mbar_wait(BAR(B_RAW_EMPTY + rslot), raw_r.phase ^ 1u);
+                            V2_STAMP(1, dbg_i); ++dbg_i;
+                            mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
+                            tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
+                                        (int)ch.c0, tc.n, BAR(B_RAW_FULL + rslot));
+                            raw_r.advance((uint32_t)p.n_raw);
                         }
                     }
                 }
@@ -371,8 +391,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         // =================================================================================================================
         // weight producer (one thread): per (stage, use, tap) one slot = [chunk 0: hi rows, lo rows][chunk 1: hi rows, lo rows]
         // =================================================================================================================
-        {
-            uint32_t w_it = 0;
+        if (elect_one()) {
+            Ring w_r;
             for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
                 const int split = (int)(tile % p.n_split);
                 for (int s = 0; s < p.n_stages; ++s) {
@@ -381,21 +401,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                         const V2Use us = st.use[u];
                         const V2Conv& cv = p.conv[us.conv];
                         const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
-                        const uint32_t piece = (uint32_t)cv.Nsl * 16u;
-                        for (int t = 0; t < ntap; ++t, ++w_it) {
-                            const int ws = w_it % p.n_w;
-                            mbar_wait(BAR(B_W_EMPTY + ws), ((w_it / p.n_w) & 1u) ^ 1u);
-                            const uint8_t* tile_g = cv.wpack + (size_t)(us.wtile + t) * ((size_t)cv.Npad * 64) + (size_t)split * piece;
+                        const int Tu = ntap == 9 ? p.T : 1;
+                        const uint32_t piece = (uint32_t)cv.Nsl * 64u;              // one tap of this filter-split part
+                        const size_t tile_b = (size_t)cv.Npad * 64;
+                        for (int t0 = 0; t0 < ntap; t0 += Tu, w_r.advance((uint32_t)p.n_w)) {
+                            const int nt = ntap - t0 < Tu ? ntap - t0 : Tu;
+                            const int ws = (int)w_r.slot;
+                            mbar_wait(BAR(B_W_EMPTY + ws), w_r.phase ^ 1u);
+                            const uint8_t* src = cv.wpack + (size_t)(us.wtile + t0) * tile_b + (size_t)split * piece;
                             const uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
-                            if (elect_one()) {
-                                mbar_arrive_expect_tx(BAR(B_W_FULL + ws), 4u * piece);
-#pragma unroll
-                                for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-                                    for (int c = 0; c < 2; ++c)
-                                        bulk_g2s(dst + (uint32_t)(c * 2 + hl) * piece, tile_g + (size_t)(hl * 2 + c) * cv.Npad * 16, piece, BAR(B_W_FULL + ws));
+                            mbar_arrive_expect_tx(BAR(B_W_FULL + ws), (uint32_t)nt * piece);
+                            if (p.n_split == 1) {
+                                bulk_g2s(dst, src, (uint32_t)nt * piece, BAR(B_W_FULL + ws));  // consecutive taps are consecutive tiles
+                            } else {
+                                for (int k = 0; k < nt; ++k) bulk_g2s(dst + (uint32_t)k * piece, src + (size_t)k * tile_b, piece, BAR(B_W_FULL + ws));
                             }
-                            __syncwarp();
                         }
                     }
                 }
@@ -408,74 +428,111 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         // one elected lane issues (tcgen05.mma / commit are single-thread instructions).
         // =================================================================================================================
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        uint32_t a_it = 0, w_it = 0, t_it = 0;
-        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
+        Ring a_r, w_r, t_r;
+        int dbg_i = 0, dbg_t = 0, dbg_w = 0;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // A: SBO = 128 B, descriptor version 1
+        const uint32_t b_hi512 = (512u >> 4) | (1u << 14), b_hi256 = (256u >> 4) | (1u << 14);  // B: SBO of hi-only / interleaved [hi|lo] rows
+        const uint32_t b_lbo = (128u >> 4) << 16;                                  // B: LBO = 128 B between the two K chunks
+        const uint32_t wait_mask = p.T == 1 ? 0x1FFu : (p.T == 3 ? 0x049u : 0x001u);
+        const uint32_t commit_mask = p.T == 1 ? 0x1FFu : (p.T == 3 ? 0x124u : 0x100u);
         const uint32_t a_lbo = (((uint32_t)p.plane_px * 16u) >> 4) << 16;          // LBO: chunk 0 -> chunk 1 plane
         const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;          // hi planes -> lo planes
         const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
-        const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
-        for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
-            const uint32_t buf = t_it % p.acc_bufs;
-            mbar_wait(BAR(B_ACC_EMPTY + buf), ((t_it / p.acc_bufs) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t acc = tmem_u + buf * tile_cols;
-            for (int s = 0; s < p.n_stages; ++s, ++a_it) {
-                const V2Stage& st = p.stage[s];
-                const uint32_t aslot = a_it % p.n_a;
-                mbar_wait(BAR(B_A_FULL + aslot), (a_it / p.n_a) & 1u);
+        const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4;
+        const uint32_t a_bytes16 = (uint32_t)p.a_bytes >> 4, w_bytes16 = (uint32_t)p.w_bytes >> 4;
+        const uint32_t n_w = (uint32_t)p.n_w, n_a = (uint32_t)p.n_a, acc_bufs = (uint32_t)p.acc_bufs;
+        const int MB = p.MB;
+        const uint32_t cols_block = (uint32_t)p.cols_block;
+        const bool dual = p.dual != 0;
+        // operand-plane offset (in 16-byte rows) of every tap: a 3x3 tap is the same plane read from a shifted start address
+        uint32_t tapoff[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            int pl = 0, shift = 0;
+            if (GEO == G_S1K3) {
+                shift = (t / 3) * p.P + (t % 3);
+            } else if (GEO == G_S2K3) {
+                const int dy = t / 3 - 1, dx = t % 3 - 1;
+                pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
+                shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
+            }
+            tapoff[t] = (uint32_t)(pl * 4 * p.plane_px + shift);
+        }
+        const uint32_t centeroff = (GEO == G_S1K3 || GEO == G_S2K3) ? (uint32_t)(p.P + 1) : 0u;
+        // ONE elected lane runs the whole role: per-block elect/reconvergence costs ~190 clk on this path (tools/umma_rate_probe.cu),
+        // and inside an elect branch the compiler still keeps the (single-lane) values in uniform registers.
+        if (elect_one()) {
+            for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
+                mbar_wait(BAR(B_ACC_EMPTY + t_r.slot), t_r.phase ^ 1u);
                 tc_fence_after();
-                const uint32_t a_base = sA_u + aslot * (uint32_t)p.a_bytes;
-                for (int u = 0; u < st.n_use; ++u) {
-                    const V2Use us = st.use[u];
-                    const V2Conv& cv = p.conv[us.conv];
-                    const int ntap = us.taps == TAPS_ALL ? cv.ntaps : 1;
-                    const uint32_t nsl = (uint32_t)cv.Nsl;
-                    const uint32_t b_lbo = ((2u * nsl * 16u) >> 4) << 16;
-                    const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
-                    const uint32_t dcol = acc + (uint32_t)cv.col;
-                    for (int t = 0; t < ntap; ++t, ++w_it) {
-                        const uint32_t ws = w_it % p.n_w;
-                        mbar_wait(BAR(B_W_FULL + ws), (w_it / p.n_w) & 1u);
-                        tc_fence_after();
-                        int pl = 0, shift = 0;
-                        if (GEO == G_S1K3) {
-                            shift = us.taps == TAPS_ALL ? (t / 3) * p.P + (t % 3) : p.P + 1;
-                        } else if (GEO == G_S2K3) {
-                            if (us.taps == TAPS_ALL) {
-                                const int dy = t / 3 - 1, dx = t % 3 - 1;
-                                pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
-                                shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
+                V2_STAMP(4, dbg_t); ++dbg_t;
+                const uint32_t acc = tmem_u + t_r.slot * tile_cols;
+                for (int s = 0; s < p.n_stages; ++s) {
+                    const V2Stage& st = p.stage[s];
+                    mbar_wait(BAR(B_A_FULL + a_r.slot), a_r.phase);
+                    tc_fence_after();
+                    V2_STAMP(2, dbg_i); ++dbg_i;
+                    const uint32_t a_base16 = (sA16 + a_r.slot * a_bytes16) | a_lbo;
+                    for (int u = 0; u < st.n_use; ++u) {
+                        const V2Use us = st.use[u];
+                        const V2Conv& cv = p.conv[us.conv];
+                        const uint32_t nsl = (uint32_t)cv.Nsl;
+                        const uint32_t piece16 = nsl * 4u;                               // one tap of weights, in 16-byte units
+                        const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
+                        const uint32_t dcol = acc + (uint32_t)cv.col;
+                        // issue every M-block of one tap: weights at b16 (16-byte units, LBO already or-ed in)
+                        auto do_tap = [&](uint32_t off, uint32_t b16, uint32_t accum) {
+                            uint32_t a0 = a_base16 + off;
+                            uint32_t d = dcol;
+                            if (dual) {  // B' = [b_hi | b_lo] interleaved per 8-filter group (SBO 256 B): all four hi/lo products in two MMAs
+#pragma unroll 4
+                                for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi256), idesc2, accum);
+                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi256), idesc2, 1u);
+                                }
                             } else {
-                                shift = p.P + 1;
-                            }
-                        }
-                        const uint32_t a_hi = ((a_base + (uint32_t)(pl * 4 * p.plane_px + shift) * 16u) >> 4) | a_lbo;
-                        const uint32_t b_hi = ((sW_u + ws * (uint32_t)p.w_bytes) >> 4) | b_lbo;
-                        const uint32_t accum = (us.first && t == 0) ? 0u : 1u;
-                        if (elect_one()) {
-                            for (int mb = 0; mb < p.MB; ++mb) {
-                                const uint32_t a0 = a_hi + (uint32_t)mb * 128u;
-                                const uint32_t d = dcol + (uint32_t)(mb * p.cols_block);
-                                if (p.dual) {
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi, desc_hi), idesc2, accum);        // [a_hi*b_hi | a_hi*b_lo]
-                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b_hi, desc_hi), idesc1, 1u);  //  + a_lo*b_hi
-                                } else {
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi, desc_hi), idesc1, accum);
-                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b_hi, desc_hi), idesc1, 1u);
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b_hi + nsl, desc_hi), idesc1, 1u);
+#pragma unroll 4
+                                for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi512), idesc1, accum);
+                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi512), idesc1, 1u);
+                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16 + 16u, b_hi512), idesc1, 1u);
                                 }
                             }
-                            mma_commit(BAR(B_W_EMPTY + ws));
+                        };
+                        if (us.taps == TAPS_ALL && cv.ntaps == 9) {
+                            uint32_t b16 = 0;
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) {
+                                if ((wait_mask >> t) & 1u) {
+                                    V2_STAMP(5, dbg_w); ++dbg_w;
+                                    mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
+                                    V2_STAMP(5, dbg_w); ++dbg_w;
+                                    b16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
+                                }
+                                do_tap(tapoff[t], b16, (us.first && t == 0) ? 0u : 1u);
+                                b16 += piece16;
+                                if ((commit_mask >> t) & 1u) {
+                                    mma_commit(BAR(B_W_EMPTY + w_r.slot));
+                                    V2_STAMP(5, dbg_w); ++dbg_w;
+                                    w_r.advance(n_w);
+                                }
+                            }
+                        } else {
+                            mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);
+                            do_tap(us.taps == TAPS_ALL ? 0u : centeroff, (sW16 + w_r.slot * w_bytes16) | b_lbo, us.first ? 0u : 1u);
+                            mma_commit(BAR(B_W_EMPTY + w_r.slot));
+                            w_r.advance(n_w);
                         }
-                        __syncwarp();
                     }
+                    mma_commit(BAR(B_A_EMPTY + a_r.slot));
+                    V2_STAMP(2, dbg_i); ++dbg_i;
+                    a_r.advance(n_a);
                 }
-                if (elect_one()) mma_commit(BAR(B_A_EMPTY + aslot));
-                __syncwarp();
+                mma_commit(BAR(B_ACC_FULL + t_r.slot));
+                t_r.advance(acc_bufs);
             }
-            if (elect_one()) mma_commit(BAR(B_ACC_FULL + buf));
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp >= 12) {
         // =================================================================================================================
         // epilogue: TMEM -> registers -> activation -> NCHW
@@ -483,14 +540,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         const int quarter = warp & 3;
         const size_t oplane = (size_t)p.Hout * p.Wout;
         const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
-        uint32_t t_it = 0;
-        for (long long tile = tile0; tile < p.n_tiles; tile += tstep, ++t_it) {
+        Ring t_r;
+        int dbg_i = 0;
+        for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
             const TileCoord tc = decode_tile(p, tile);
-            const uint32_t buf = t_it % p.acc_bufs;
-            mbar_wait(BAR(B_ACC_FULL + buf), (t_it / p.acc_bufs) & 1u);
+            const uint32_t buf = t_r.slot;
+            mbar_wait(BAR(B_ACC_FULL + buf), t_r.phase);
+            if (tid == 12 * 32) { V2_STAMP(3, dbg_i); ++dbg_i; }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * tile_cols + ((uint32_t)(quarter * 32) << 16);
-            for (int mb = 0; mb < p.MB; ++mb) {
+            for (int mb = 0; mb < ((p.exp & 4) ? 0 : p.MB); ++mb) {
                 const int q = mb * 128 + quarter * 32 + lane;
                 const int oyl = q / p.P, oxl = q - oyl * p.P;
                 const int oy = tc.oy0 + oyl, ox = tc.ox0 + oxl;
@@ -499,29 +558,41 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                 for (int j = 0; j < p.n_convs; ++j) {
                     const V2Conv& cv = p.conv[j];
                     const int f0 = tc.split * cv.Nsl;
-                    float* dst = cv.out + (size_t)tc.n * cv.out_stride_n + pix;
+                    const int nf = cv.F - f0 < cv.Nsl ? cv.F - f0 : cv.Nsl;  // real filters of this split part (may be <= 0)
+                    float* dst = cv.out + (size_t)tc.n * cv.out_stride_n + (size_t)f0 * oplane + pix;
                     const uint32_t tcol = acc + (uint32_t)(mb * p.cols_block + cv.col);
-                    for (int c = 0; c < cv.Nsl; c += 16) {
-                        uint32_t r[16];
-                        tmem_ld_x16(tcol + (uint32_t)c, r);
-                        if (p.dual) {
-                            uint32_t r2[16];
-                            tmem_ld_x16(tcol + (uint32_t)(cv.Nsl + c), r2);
+                    const bool act = cv.act != 0;
+                    for (int c = 0; c < nf; c += 16, dst += 16 * oplane) {
+                        float o[16];
+                        if (p.dual) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
+                            uint32_t r0[16], r1[16];
+                            tmem_ld_x16(tcol + (uint32_t)(2 * c), r0);
+                            tmem_ld_x16(tcol + (uint32_t)(2 * c + 16), r1);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+                            for (int k = 0; k < 8; ++k) {
+                                o[k] = __uint_as_float(r0[k]) + __uint_as_float(r0[k + 8]);
+                                o[k + 8] = __uint_as_float(r1[k]) + __uint_as_float(r1[k + 8]);
+                            }
                         } else {
+                            uint32_t r0[16];
+                            tmem_ld_x16(tcol + (uint32_t)c, r0);
                             tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(r0[k]);
+                        }
+                        if (act) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) o[k] = leaky(o[k], p.slope);
                         }
                         if (valid) {
+                            if (c + 16 <= nf) {
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                const int f = f0 + c + k;
-                                if (f < cv.F) {
-                                    float o = __uint_as_float(r[k]);
-                                    if (cv.act) o = leaky(o, p.slope);
-                                    dst[(size_t)f * oplane] = o;
-                                }
+                                for (int k = 0; k < 16; ++k) dst[(size_t)k * oplane] = o[k];
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    if (c + k < nf) dst[(size_t)k * oplane] = o[k];
                             }
                         }
                     }
@@ -530,6 +601,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
+            if (tid == 12 * 32) { V2_STAMP(3, dbg_i); ++dbg_i; }
+            t_r.advance((uint32_t)p.acc_bufs);
         }
     }
     tc_fence_before();
@@ -573,10 +646,9 @@ bool make_map4(CUtensorMap* tm, const ConvSrcDev& s, int N, int bw, int bh) {
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-double mma_cycles(int N) {  // measured, profiles/r01_umma_probe.md
-    double c = N / 2.0, s = 32.0 + N / 4.0;
-    c = c > s ? c : s;
-    return c > 47.0 ? c : 47.0;
+double mma_cycles(int N) {  // measured with a lean single-lane issue loop, tools/umma_rate_probe.cu (profiles/r01_umma_rate_probe.log)
+    const double c = N / 2.0, s = 44.0 + N / 6.0;
+    return c > s ? c : s;
 }
 
 struct V2Plan {  // what the tile search decides
@@ -617,7 +689,12 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     const int raw0 = p.BW[0] * p.BH[0] * 32, raw1 = has_up ? p.BW[1] * p.BH[1] * 32 : 0;
     p.raw_bytes = roundup(raw0 > raw1 ? raw0 : raw1, 128);
     p.a_bytes = roundup(p.n_planes * 4 * p.plane_px * 16, 128);
-    p.w_bytes = roundup(max_nsl * 64, 128);
+    // weight-ring slot: as many taps of a 3x3 use as fit ~24 KB (one barrier round trip and one bulk copy per slot)
+    p.T = max_nsl * 64 * 9 <= 24 * 1024 ? 9 : (max_nsl * 64 * 3 <= 24 * 1024 ? 3 : 1);
+    bool any9 = false;
+    for (int j = 0; j < p.n_convs; ++j) any9 = any9 || p.conv[j].ntaps == 9;
+    if (!any9) p.T = 1;
+    p.w_bytes = roundup(max_nsl * 64 * p.T, 128);
     p.tiles_x = cdiv(p.Wout, TW);
     p.tiles_y = cdiv(p.Hout, R);
     p.n_tiles = (long long)p.N * p.tiles_x * p.tiles_y * n_split;
@@ -657,7 +734,7 @@ V2Plan search_plan(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunk
                     const V2Use& us = p.stage[s].use[u];
                     const int nsl = p.conv[us.conv].Npad / n_split;
                     const int nt = us.taps == TAPS_ALL ? p.conv[us.conv].ntaps : 1;
-                    mma_mb += nt * (dual ? mma_cycles(2 * nsl) + mma_cycles(nsl) : 3.0 * mma_cycles(nsl));
+                    mma_mb += nt * (dual ? 2.0 * mma_cycles(2 * nsl) : 3.0 * mma_cycles(nsl));
                     wbytes += (double)nt * nsl * 64.0;
                 }
             int last_tw = -1;
@@ -752,6 +829,13 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
 
     const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
     KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
+    static const int exp_flags = getenv("KBNET_V2_EXP") ? atoi(getenv("KBNET_V2_EXP")) : 0;
+    p.exp = exp_flags;
+    static const char* timeline = getenv("KBNET_V2_TIMELINE");  // debugging aid: dump clock64 stamps of CTA 0 to this file (synchronises!)
+    if (timeline) {
+        KB_CUDA(cudaMalloc(&p.dbg, 6 * 4096 * sizeof(long long)));
+        KB_CUDA(cudaMemsetAsync(p.dbg, 0, 6 * 4096 * sizeof(long long), stream));
+    }
     static const bool debug = getenv("KBNET_V2_DEBUG") != nullptr;
     if (debug)
         fprintf(stderr, "[conv v2] geo %d  %dx%dx%d -> %dx%d  stages %d convs %d Npad %d/%d/%d | R %d TW %d P %d MB %d split %d dual %d | tiles %lld grid %lld | "
@@ -771,6 +855,19 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
     KB_CUDA(cudaGetLastError());
     count_launch();
     count_launch_v2();
+    if (timeline) {
+        std::vector<long long> h(6 * 4096);
+        KB_CUDA(cudaStreamSynchronize(stream));
+        KB_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.dbg);
+        if (FILE* f = fopen(timeline, "w")) {
+            fprintf(f, "# stages %d chunks_tma_per_tile ? MB %d n_a %d n_raw %d n_w %d acc_bufs %d tiles %lld grid %lld\n", p.n_stages, p.MB, p.n_a, p.n_raw, p.n_w,
+                    p.acc_bufs, p.n_tiles, grid);
+            for (int r = 0; r < 6; ++r)
+                for (int i = 0; i < 4096 && h[r * 4096 + i]; ++i) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
+            fclose(f);
+        }
+    }
     return 0;
 }
 

@@ -46,7 +46,7 @@ struct UmmaConvParams {
     int F, Npad, n_parts, part_N;
     int n_groups, n_stages;
     uint32_t groups[UM_MAX_GROUPS];  // src | nch << 8 | c0 << 16
-    const uint8_t* wpack;            // [n_stages][taps][Npad * 64 B]
+    const uint8_t* wpack;            // [n_stages][taps][Npad * 64 B], tile layout in pack_weights_kernel
     float* out;
     long long out_stride_n;
     int act;
@@ -100,10 +100,13 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
     if (n < p.F && e < nch) v = __ldg(p.w + ((size_t)n * p.Ctot + p.seg_off[src] + c0 + e) * p.taps + t);
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    // tile = [g = n / 8][hi | lo][chunk 0 | 1][8 rows][16 B]: any range of filter groups is contiguous (filter splits load with ONE
+    // bulk copy), and every operand form is a K-major no-swizzle descriptor: LBO = 128 B between the K chunks, SBO = 512 B between
+    // 8-filter groups (hi or lo rows alone), SBO = 256 B for the interleaved [hi | lo] rows of the "dual" MMA.
     uint8_t* tile = p.out + ((size_t)s * p.taps + t) * ((size_t)p.Npad * 64);
-    const size_t off = ((size_t)c * p.Npad + n) * 16 + e * 2;
+    const size_t off = (size_t)(n >> 3) * 512 + (size_t)c * 128 + (size_t)(n & 7) * 16 + e * 2;
     *reinterpret_cast<__nv_bfloat16*>(tile + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(tile + (size_t)p.Npad * 32 + off) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(tile + off + 256) = lo;
 }
 
 size_t conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize) {
@@ -329,9 +332,9 @@ __global__ void __launch_bounds__(UM_THREADS, 2) conv_umma_kernel(const __grid_c
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16_f32(128, p.part_N);
             const uint64_t adesc0 = smem_desc(0, (uint32_t)p.plane_px * 16u, 128u);
-            const uint64_t bdesc0 = smem_desc(0, (uint32_t)p.Npad * 16u, 128u);
+            const uint64_t bdesc0 = smem_desc(0, 128u, 512u);  // packed tile layout: see pack_weights_kernel
             const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;
-            const uint32_t b_lo_off = ((uint32_t)p.Npad * 32u) >> 4;
+            const uint32_t b_lo_off = 256u >> 4;
             uint32_t wp = 0;
             for (int s = 0; s < p.n_stages; ++s) {
                 const int slot = s % p.a_stages;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) conv_umma_kernel(const __grid_c
                         const uint64_t ad_hi = adesc0 + (uint64_t)(a_hi + (uint32_t)mb * 128u);
                         const uint64_t ad_lo = ad_hi + a_lo_off;
                         for (int pi = 0; pi < p.n_parts; ++pi) {
-                            const uint64_t bd_hi = bdesc0 + (uint64_t)(w_hi + (uint32_t)(pi * p.part_N));
+                            const uint64_t bd_hi = bdesc0 + (uint64_t)(w_hi + (uint32_t)(pi * p.part_N) * 4u);
                             const uint64_t bd_lo = bd_hi + b_lo_off;
                             const uint32_t d = tmem_base + (uint32_t)(mb * p.Npad + pi * p.part_N);
                             mma_bf16_ss(d, ad_hi, bd_hi, idesc, (s | t) ? 1u : 0u);
