@@ -485,13 +485,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                             uint32_t a0 = a_base16 + off;
                             uint32_t d = dcol;
                             if (dual) {  // B' = [b_hi | b_lo] interleaved per 8-filter group (SBO 256 B): all four hi/lo products in two MMAs
-#pragma unroll 4
+#pragma unroll 2
                                 for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
                                     mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi256), idesc2, accum);
                                     mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi256), idesc2, 1u);
                                 }
                             } else {
-#pragma unroll 4
+#pragma unroll 2
                                 for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
                                     mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi512), idesc1, accum);
                                     mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi512), idesc1, 1u);
@@ -562,24 +562,32 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     float* dst = cv.out + (size_t)tc.n * cv.out_stride_n + (size_t)f0 * oplane + pix;
                     const uint32_t tcol = acc + (uint32_t)(mb * p.cols_block + cv.col);
                     const bool act = cv.act != 0;
+                    if (nf <= 0) continue;
+                    // batches of 16 filters; the TMEM load of batch b+1 is in flight while batch b is activated and stored
+                    uint32_t r0[16], r1[16];
+                    if (p.dual) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
+                        tmem_ld_x16(tcol, r0);
+                        tmem_ld_x16(tcol + 16u, r1);
+                    } else {
+                        tmem_ld_x16(tcol, r0);
+                    }
                     for (int c = 0; c < nf; c += 16, dst += 16 * oplane) {
                         float o[16];
-                        if (p.dual) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
-                            uint32_t r0[16], r1[16];
-                            tmem_ld_x16(tcol + (uint32_t)(2 * c), r0);
-                            tmem_ld_x16(tcol + (uint32_t)(2 * c + 16), r1);
-                            tmem_ld_wait();
+                        tmem_ld_wait();
+                        if (p.dual) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 o[k] = __uint_as_float(r0[k]) + __uint_as_float(r0[k + 8]);
                                 o[k + 8] = __uint_as_float(r1[k]) + __uint_as_float(r1[k + 8]);
                             }
+                            if (c + 16 < nf) {
+                                tmem_ld_x16(tcol + (uint32_t)(2 * c + 32), r0);
+                                tmem_ld_x16(tcol + (uint32_t)(2 * c + 48), r1);
+                            }
                         } else {
-                            uint32_t r0[16];
-                            tmem_ld_x16(tcol + (uint32_t)c, r0);
-                            tmem_ld_wait();
 #pragma unroll
                             for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(r0[k]);
+                            if (c + 16 < nf) tmem_ld_x16(tcol + (uint32_t)(c + 16), r0);
                         }
                         if (act) {
 #pragma unroll

@@ -31,7 +31,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+// (not unrolled: every wait site would otherwise expand to dozens of try_wait copies and the warp-specialised kernels, whose roles
+//  run different code at the same time, become instruction-fetch bound -- ncu stall_no_inst)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 24); ++i)
         if (mbar_try_wait(bar, parity)) return;
     __trap();

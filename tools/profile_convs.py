@@ -15,6 +15,7 @@ LAYERS = {  # name: (sources [(C,H,W,mode)], F, k, stride)
     'deconv1_conv': ([(64, 176, 608, 0), (64, 176, 608, 0)], 64, 3, 1),
     'deconv0_deconv': ([(64, 176, 608, 1)], 12, 3, 1),
     'deconv4_conv': ([(256, 22, 76, 0), (512, 22, 76, 0)], 256, 3, 1),
+    'conv0_depth': ([(8, 352, 1216, 0)], 16, 3, 1),
     'output0': ([(12, 352, 1216, 0)], 1, 3, 1),
     'deconv0_conv': ([(12, 352, 1216, 0)], 12, 3, 1),
 }
