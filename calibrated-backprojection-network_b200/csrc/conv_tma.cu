@@ -161,7 +161,7 @@ __device__ __forceinline__ TileCoord decode_tile(const V2Params& p, long long ti
     return t;
 }
 
-template <int GEO>
+template <int GEO, bool DUAL>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ V2Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                 mbar_wait(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
                 if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
                 uint8_t* A = sA + (size_t)aslot * p.a_bytes;
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     const V2Chunk ch = st.ch[h];
                     const int kind = ch.kind;
@@ -443,21 +443,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         const uint32_t n_w = (uint32_t)p.n_w, n_a = (uint32_t)p.n_a, acc_bufs = (uint32_t)p.acc_bufs;
         const int MB = p.MB;
         const uint32_t cols_block = (uint32_t)p.cols_block;
-        const bool dual = p.dual != 0;
-        // operand-plane offset (in 16-byte rows) of every tap: a 3x3 tap is the same plane read from a shifted start address
-        uint32_t tapoff[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            int pl = 0, shift = 0;
-            if (GEO == G_S1K3) {
-                shift = (t / 3) * p.P + (t % 3);
-            } else if (GEO == G_S2K3) {
-                const int dy = t / 3 - 1, dx = t % 3 - 1;
-                pl = (dy != 0 ? 2 : 0) + (dx != 0 ? 1 : 0);
-                shift = (dy == -1 ? 0 : 1) * p.P + (dx == -1 ? 0 : 1);
-            }
-            tapoff[t] = (uint32_t)(pl * 4 * p.plane_px + shift);
-        }
+        constexpr bool dual = DUAL;
+        // operand-plane offset (in 16-byte rows) of tap t: a 3x3 tap is the same plane read from a shifted start address
+        const uint32_t P_u = (uint32_t)p.P, plane4 = 4u * (uint32_t)p.plane_px;
+        auto tap_offset = [&](uint32_t t) -> uint32_t {
+            const uint32_t ky = (t * 11u) >> 5, kx = t - 3u * ky;  // t / 3, t % 3 for t < 9
+            if (GEO == G_S1K3) return ky * P_u + kx;
+            if (GEO == G_S2K3)  // dy = ky - 1, dx = kx - 1: parity plane (dy != 0, dx != 0), shift (dy >= 0) * P + (dx >= 0)
+                return ((ky != 1u ? 2u : 0u) + (kx != 1u ? 1u : 0u)) * plane4 + (ky != 0u ? P_u : 0u) + (kx != 0u ? 1u : 0u);
+            return 0u;
+        };
         const uint32_t centeroff = (GEO == G_S1K3 || GEO == G_S2K3) ? (uint32_t)(p.P + 1) : 0u;
         // ONE elected lane runs the whole role: per-block elect/reconvergence costs ~190 clk on this path (tools/umma_rate_probe.cu),
         // and inside an elect branch the compiler still keeps the (single-lane) values in uniform registers.
@@ -501,15 +496,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                         };
                         if (us.taps == TAPS_ALL && cv.ntaps == 9) {
                             uint32_t b16 = 0;
-#pragma unroll
-                            for (int t = 0; t < 9; ++t) {
+#pragma unroll 1
+                            for (uint32_t t = 0; t < 9; ++t) {
                                 if ((wait_mask >> t) & 1u) {
                                     V2_STAMP(5, dbg_w); ++dbg_w;
                                     mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
                                     V2_STAMP(5, dbg_w); ++dbg_w;
                                     b16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
                                 }
-                                do_tap(tapoff[t], b16, (us.first && t == 0) ? 0u : 1u);
+                                do_tap(tap_offset(t), b16, (us.first && t == 0) ? 0u : 1u);
                                 b16 += piece16;
                                 if ((commit_mask >> t) & 1u) {
                                     mma_commit(BAR(B_W_EMPTY + w_r.slot));
@@ -565,7 +560,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     if (nf <= 0) continue;
                     // batches of 16 filters; the TMEM load of batch b+1 is in flight while batch b is activated and stored
                     uint32_t r0[16], r1[16];
-                    if (p.dual) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
+                    if (DUAL) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
                         tmem_ld_x16(tcol, r0);
                         tmem_ld_x16(tcol + 16u, r1);
                     } else {
@@ -574,7 +569,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     for (int c = 0; c < nf; c += 16, dst += 16 * oplane) {
                         float o[16];
                         tmem_ld_wait();
-                        if (p.dual) {
+                        if (DUAL) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 o[k] = __uint_as_float(r0[k]) + __uint_as_float(r0[k + 8]);
@@ -850,10 +845,15 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
                 "raw %d x %d B, A %d x %d B, W %d x %d B, smem %lld | tmem %d cols x %d bufs\n",
                 geo, p.N, p.Hin, p.Win, p.Hout, p.Wout, p.n_stages, p.n_convs, p.conv[0].Npad, p.conv[1].Npad, p.conv[2].Npad, p.R, p.TW, p.P, p.MB,
                 p.n_split, p.dual, p.n_tiles, grid, p.n_raw, p.raw_bytes, p.n_a, p.a_bytes, p.n_w, p.w_bytes, used, p.MB * p.cols_block, p.acc_bufs);
-#define V2_LAUNCH(G)                                                                                                  \
-    do {                                                                                                              \
-        KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));     \
-        conv_v2_kernel<G><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                             \
+#define V2_LAUNCH(G)                                                                                                          \
+    do {                                                                                                                      \
+        if (p.dual) {                                                                                                         \
+            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));   \
+            conv_v2_kernel<G, true><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                           \
+        } else {                                                                                                              \
+            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));  \
+            conv_v2_kernel<G, false><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                          \
+        }                                                                                                                     \
     } while (0)
     if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
     else if (geo == G_S1K1) V2_LAUNCH(G_S1K1);
