@@ -39,6 +39,14 @@ def synth_inputs(n, seed):
     return image, depth, valid, k
 
 
+def ncu_traffic(key):
+    """dram bytes of one launch of the kernel, from the committed ncu capture (profiles/r01_traffic.json); None if absent"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))[key]['traffic'])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -181,6 +189,20 @@ def main():
         return y
     s2d_mod.forward = timed_s2d
 
+    # ... and around KB block 2 (BASELINE config 2 is exactly this call at 8 frames: 48/16/48 ch @176x608 -> 96/32/96 @88x304)
+    kb_events = []
+    kb2 = model.encoder.calibrated_backprojection2
+    kb2_forward = kb2.forward
+
+    def timed_kb2(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = kb2_forward(*a, **kw)
+        e1.record()
+        kb_events.append((e0, e1))
+        return y
+    kb2.forward = timed_kb2
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -190,6 +212,7 @@ def main():
         model.forward(*resident)
     barrier()
     s2d_events.clear()
+    kb_events.clear()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -203,24 +226,51 @@ def main():
     launches = lib.kbnet_launch_count() - n0
     ms = e0.elapsed_time(e1)
     s2d_ms = sum(a.elapsed_time(b) for a, b in s2d_events) / max(len(s2d_events), 1)
+    kb_ms = sum(a.elapsed_time(b) for a, b in kb_events) / max(len(kb_events), 1)
+    tma_launches = lib.kbnet_tma_engine_launch_count()
 
-    # end-to-end: pinned host inputs -> H2D -> forward -> D2H of the dense depth, every step
-    for _ in range(2):
-        out_host.copy_(model.forward(*[t.to(dev, non_blocking=True) for t in host]), non_blocking=True)
+    # end-to-end through the public API: every step copies ITS inputs from pinned host memory and reads ITS result back.
+    # Two device input sets + a copy stream: the H2D of step i+1 overlaps the forward of step i (the usual serving pipeline).
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(in_free[slot])
+            for d, h in zip(dev_in[slot], host):
+                d.copy_(h, non_blocking=True)
+            in_ready[slot].record(copy_stream)
+
+    def e2e_loop(n_steps):
+        for ev in in_free:
+            ev.record(main_stream)
+        upload(0)
+        for i in range(n_steps):
+            slot = i & 1
+            if i + 1 < n_steps:
+                upload(slot ^ 1)
+            main_stream.wait_event(in_ready[slot])
+            out_host.copy_(model.forward(*dev_in[slot]), non_blocking=True)
+            in_free[slot].record(main_stream)
+
+    e2e_loop(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        out_host.copy_(model.forward(*[t.to(dev, non_blocking=True) for t in host]), non_blocking=True)
+    e2e_loop(args.steps)
+    copy_stream.synchronize()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.summary() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, s2d_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, s2d_ms, kb_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, s2d_ms = (float(v) for v in t.tolist())
+        ms, ms_e2e, s2d_ms, kb_ms = (float(v) for v in t.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -232,6 +282,10 @@ def main():
     hbm_peak, tf_peak, tf_sus, peak_kind = peaks()
     s2d_bytes = 4.0 * H * W * (2 + 8) * nb                    # 4*H*W*(C_in + n_filter) per frame
     s2d_gbs = s2d_bytes / (s2d_ms * 1e-3) / 1e9 if s2d_ms > 0 else 0.0
+    # KB block 2 (fast path): image 48ch + depth 16ch full reads, fused 48ch at even pixels, three outputs
+    kb_bytes = 4.0 * nb * ((48 + 16) * 176 * 608 + 48 * 88 * 304 + (96 + 32 + 96) * 88 * 304)
+    kb_flops = 24.19e9 * nb / 8.0
+    kb_gbs = kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -239,14 +293,23 @@ def main():
         'config': {'workload': 'kbnet_kitti_352x1216_full_forward', 'frames_per_gpu_per_step': nb, 'global_batch': nb * world,
                    'pools': {'min': MIN_POOLS, 'max': MAX_POOLS}, 'parallelism': 'batch-sharded x%d, weights broadcast once (%d B)' % (world, bcast_bytes),
                    'conv_backend_outside_hot_path': M.CONV_BACKEND,
-                   'l2': 'per-step activations (>2 GB at batch 8) far exceed the 126 MB L2; no explicit flush'},
+                   'l2': 'per-step activations (>2 GB at batch 8) far exceed the 126 MB L2; no explicit flush',
+                   'e2e_pipeline': 'double-buffered pinned H2D on a copy stream overlapped with the previous forward; D2H of every result'},
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'kernel': 's2d_fused_kernel', 'bound': 'hbm', 'achieved': s2d_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': s2d_gbs / hbm_peak, 'traffic': None, 'peak_kind': peak_kind,
-                     'algorithmic_bytes_per_launch': s2d_bytes, 'ms_per_launch': s2d_ms},
+                     'frac': s2d_gbs / hbm_peak, 'traffic': ncu_traffic('s2d_fused_kernel') if nb == 8 else None, 'peak_kind': peak_kind,
+                     'algorithmic_bytes_per_launch': s2d_bytes, 'ms_per_launch': s2d_ms,
+                     'traffic_note': 'dram__bytes_read+write of one launch, ncu --set full, profiles/r01_traffic.json'},
+        'roofline_kb': {'kernel': 'conv_v2_kernel<S2K3> (fused KB block 2 = BASELINE config 2)', 'bound': 'hbm', 'achieved': kb_gbs,
+                        'peak': hbm_peak, 'unit': 'GB/s', 'frac': kb_gbs / hbm_peak, 'traffic': ncu_traffic('kb_block2_fused') if nb == 8 else None,
+                        'peak_kind': peak_kind,
+                        'algorithmic_bytes_per_launch': kb_bytes, 'ms_per_launch': kb_ms,
+                        'tensor_tflops_bf16_issued': 3.0 * kb_flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0,
+                        'tensor_peak_tflops': tf_sus},
+        'tma_engine_launches_total': int(tma_launches),
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

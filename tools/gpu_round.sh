@@ -24,6 +24,10 @@ launches)
 ncu_s2d)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2d_fused -s 3 -c 1 -o gpurun_out/prof_s2d -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_s2d.log 2>&1
   ncu -i gpurun_out/prof_s2d.ncu-rep --page raw --csv > gpurun_out/prof_s2d_raw.csv 2>/dev/null;;
+ncu_kb)
+  # the fused KB block on BASELINE config 2 (tools/bench_kb.py launches nothing else from the tensor-core engine)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_v2 -s 6 -c 1 -o gpurun_out/prof_kb2 -f python tools/bench_kb.py > gpurun_out/ncu_kb.log 2>&1
+  ncu -i gpurun_out/prof_kb2.ncu-rep --page raw --csv > gpurun_out/prof_kb2_raw.csv 2>/dev/null;;
 ncu_conv)
   # one full forward = 34 conv launches; skip the 3 warm-up forwards, capture a spread of layers
   timeout 900 ncu --set full --clock-control none -k regex:conv_umma -s 102 -c 34 -o gpurun_out/prof_conv -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
