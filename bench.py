@@ -138,6 +138,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=2, help='frames per step of the CPU reference sample')
     ap.add_argument('--conv-backend', default=None, choices=['kbnet', 'torch'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-autotune', action='store_true')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -161,6 +162,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     torch.set_grad_enabled(False)
     lib = kbnet_b200._lib.load()
+    kbnet_b200.set_autotune(not args.no_autotune)     # tile plans are measured during the warm-up steps
 
     torch.manual_seed(0 if rank == 0 else 1234 + rank)         # only rank 0's weights survive the broadcast
     model = kbnet_b200.KBNetModel(3, 2, MIN_POOLS, MAX_POOLS, 3, 8, F_IMG, F_DEP, [0, 1, 2, 3], F_DEC, deconv_type='up',
@@ -292,10 +294,10 @@ def main():
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'kbnet_kitti_352x1216_full_forward', 'frames_per_gpu_per_step': nb, 'global_batch': nb * world,
                    'pools': {'min': MIN_POOLS, 'max': MAX_POOLS}, 'parallelism': 'batch-sharded x%d, weights broadcast once (%d B)' % (world, bcast_bytes),
-                   'conv_backend_outside_hot_path': M.CONV_BACKEND,
+                   'conv_backend_outside_hot_path': M.CONV_BACKEND, 'tile_autotune': not args.no_autotune,
                    'l2': 'per-step activations (>2 GB at batch 8) far exceed the 126 MB L2; no explicit flush',
                    'e2e_pipeline': 'double-buffered pinned H2D on a copy stream overlapped with the previous forward; D2H of every result'},
-        'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+        'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks,

@@ -9,11 +9,17 @@ from .modules import CalibratedBackprojectionBlock, SparseToDensePool, install, 
 from .model import KBNetEncoder, KBNetModel, MultiScaleDecoder
 
 __all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
-           'install', 'set_precision', 'get_precision', 'ops', 'dist', 'build_library', 'library_path']
+           'install', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']
 
 
 def build_library(force=False, verbose=False):
     return _build.build(force=force, verbose=verbose)
+
+
+def set_autotune(on=True):
+    """Measured tile selection for the tensor-core engine: the first call for each new layer shape times the best candidate
+    tilings (synchronising once) and caches the winner.  Off by default."""
+    _lib.load().kbnet_set_autotune(1 if on else 0)
 
 
 def library_path():

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
 
-EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
+EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_set_autotune', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
            'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights', 'kbnet_intrinsics_inverse')
 
 
@@ -34,6 +34,8 @@ def load():
     lib.kbnet_last_error.restype = c.c_char_p
     lib.kbnet_launch_count.restype = c.c_ulonglong
     lib.kbnet_tma_engine_launch_count.restype = c.c_ulonglong
+    lib.kbnet_set_autotune.restype = None
+    lib.kbnet_set_autotune.argtypes = [i]
     lib.kbnet_s2d_forward.restype = i
     lib.kbnet_s2d_forward.argtypes = [vp, i, i, i, i, c.POINTER(i), i, c.POINTER(i), i, c.POINTER(vp), i, i, vp, vp, f, vp, vp, vp]
     lib.kbnet_s2d_wpack_bytes.restype = sz

@@ -53,6 +53,7 @@ int kbnet_version(void) { return KBNET_B200_VERSION; }
 const char* kbnet_last_error(void) { return g_err; }
 
 unsigned long long kbnet_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+void kbnet_set_autotune(int on) { set_autotune(on); }
 unsigned long long kbnet_tma_engine_launch_count(void) { return __atomic_load_n(&g_launches_v2, __ATOMIC_RELAXED); }
 
 int kbnet_s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,

@@ -71,6 +71,7 @@ size_t conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize);
 int conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, cudaStream_t stream);
 // second-generation engine (conv_tma.cu): persistent, TMA-fed; takes the same packed weights as conv_umma.cu
 bool conv_v2_supported(const ConvParams& p);
+void set_autotune(int on);
 int conv_v2_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
 bool kb_fused_supported(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
                         const float* coordinates, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);

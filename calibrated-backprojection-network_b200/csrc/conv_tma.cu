@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -717,11 +718,16 @@ struct PlanEntry {
 std::mutex g_plan_mutex;
 std::vector<PlanEntry> g_plans;
 
-V2Plan search_plan(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunks, int sms) {
+// Candidate plans ordered by the cost model: the best (R) for every (filter split, split mode, tile width), cheapest first.
+struct Candidate {
+    V2Plan plan;
+    double cost;
+};
+std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunks, int sms) {
     const int geo = p.geo;
-    double best = 1e300;
-    V2Plan plan = {0, 0, 0, 0};
-    V2Params trial = p;
+    std::vector<Candidate> cands;
+    static thread_local V2Params trial;
+    trial = p;
     const int tw_step = geo == G_S1K3 ? (has_up ? 8 : 4) : (geo == G_S1K1 ? 4 : 2);
     const int r_step = (geo == G_S1K3 && has_up) ? 2 : 1;
     for (int n_split = 1; n_split <= 8; n_split *= 2) {
@@ -746,6 +752,8 @@ V2Plan search_plan(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunk
                 if (TW > 248) continue;
                 if (TW == last_tw) continue;
                 last_tw = TW;
+                double best = 1e300;
+                V2Plan plan = {0, 0, 0, 0};
                 for (int R = r_step; R <= 64; R += r_step) {
                     if (R - r_step >= p.Hout) break;
                     const long long smem_min = apply_geometry(trial, R, TW, n_split, dual, has_up);
@@ -765,10 +773,85 @@ V2Plan search_plan(const V2Params& p, bool has_up, int n_chunks, int n_tma_chunk
                     const double total = waves * tile + tile + 4000.0;  // + pipeline fill
                     if (total < best) { best = total; plan = {R, TW, n_split, dual}; }
                 }
+                if (plan.R > 0) cands.push_back({plan, best});
             }
         }
     }
-    return plan;
+    std::sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) { return a.cost < b.cost; });
+    return cands;
+}
+
+int g_autotune = -1;  // -1: not initialised (KBNET_AUTOTUNE), 0 off, 1 on
+
+// geometry + rings + tensor maps + launch for one plan
+int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, int sms,
+                     cudaStream_t stream, bool report) {
+    const int geo = p.geo;
+    long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
+    KB_CHECK_ARG(used > 0 && used <= V2_SMEM_LIMIT, "conv(v2): plan R=%d TW=%d split=%d dual=%d does not fit", plan.R, plan.TW, plan.n_split, plan.dual);
+    p.n_raw = 2; p.n_a = 2; p.n_w = 2;
+    // spend the remaining shared memory: weights slots first (cheap), then raw slots, then a third A slot
+    while (p.n_w < V2_MAX_W && p.n_w < 4 && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
+    while (p.n_raw < 4 && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
+    if (p.n_stages > 2 && used + p.a_bytes <= V2_SMEM_LIMIT) { ++p.n_a; used += p.a_bytes; }
+    while (p.n_w < V2_MAX_W && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
+    while (p.n_raw < V2_MAX_RAW && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
+    if (used < 120 * 1024) used = 120 * 1024;  // one CTA per SM (the TMEM budget assumes it)
+
+    V2Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int i = 0; i < n_maps; ++i)
+        KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]]), "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
+
+    const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
+    KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
+    static const int exp_flags = getenv("KBNET_V2_EXP") ? atoi(getenv("KBNET_V2_EXP")) : 0;
+    p.exp = exp_flags;
+    static const char* timeline = getenv("KBNET_V2_TIMELINE");  // debugging aid: dump clock64 stamps of CTA 0 to this file (synchronises!)
+    p.dbg = nullptr;
+    if (timeline && report) {
+        KB_CUDA(cudaMalloc(&p.dbg, 6 * 4096 * sizeof(long long)));
+        KB_CUDA(cudaMemsetAsync(p.dbg, 0, 6 * 4096 * sizeof(long long), stream));
+    }
+    static const bool debug = getenv("KBNET_V2_DEBUG") != nullptr;
+    if (debug && report)
+        fprintf(stderr, "[conv v2] geo %d  %dx%dx%d -> %dx%d  stages %d convs %d Npad %d/%d/%d | R %d TW %d P %d MB %d split %d dual %d T %d | tiles %lld grid %lld | "
+                "raw %d x %d B, A %d x %d B, W %d x %d B, smem %lld | tmem %d cols x %d bufs\n",
+                geo, p.N, p.Hin, p.Win, p.Hout, p.Wout, p.n_stages, p.n_convs, p.conv[0].Npad, p.conv[1].Npad, p.conv[2].Npad, p.R, p.TW, p.P, p.MB,
+                p.n_split, p.dual, p.T, p.n_tiles, grid, p.n_raw, p.raw_bytes, p.n_a, p.a_bytes, p.n_w, p.w_bytes, used, p.MB * p.cols_block, p.acc_bufs);
+#define V2_LAUNCH(G)                                                                                                          \
+    do {                                                                                                                      \
+        if (p.dual) {                                                                                                         \
+            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));   \
+            conv_v2_kernel<G, true><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                           \
+        } else {                                                                                                              \
+            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));  \
+            conv_v2_kernel<G, false><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                          \
+        }                                                                                                                     \
+    } while (0)
+    if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
+    else if (geo == G_S1K1) V2_LAUNCH(G_S1K1);
+    else if (geo == G_S2K3) V2_LAUNCH(G_S2K3);
+    else V2_LAUNCH(G_S2K1);
+#undef V2_LAUNCH
+    KB_CUDA(cudaGetLastError());
+    count_launch();
+    count_launch_v2();
+    if (p.dbg) {
+        std::vector<long long> h(6 * 4096);
+        KB_CUDA(cudaStreamSynchronize(stream));
+        KB_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.dbg);
+        p.dbg = nullptr;
+        if (FILE* f = fopen(timeline, "w")) {
+            fprintf(f, "# stages %d MB %d n_a %d n_raw %d n_w %d acc_bufs %d tiles %lld grid %lld\n", p.n_stages, p.MB, p.n_a, p.n_raw, p.n_w, p.acc_bufs,
+                    p.n_tiles, grid);
+            for (int r = 0; r < 6; ++r)
+                for (int i = 0; i < 4096 && h[r * 4096 + i]; ++i) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
+            fclose(f);
+        }
+    }
+    return 0;
 }
 
 int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, cudaStream_t stream) {
@@ -790,13 +873,14 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
             if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
         }
     }
+    if (g_autotune < 0) g_autotune = getenv("KBNET_AUTOTUNE") ? atoi(getenv("KBNET_AUTOTUNE")) : 0;
     PlanKey key;
     memset(&key, 0, sizeof(key));
     {
         int* k = key.v;
         k[0] = geo; k[1] = p.N; k[2] = p.Hin; k[3] = p.Win; k[4] = p.Hout; k[5] = p.Wout; k[6] = p.n_stages; k[7] = p.n_convs;
         for (int j = 0; j < p.n_convs; ++j) { k[8 + 2 * j] = p.conv[j].Npad; k[9 + 2 * j] = p.conv[j].ntaps; }
-        k[14] = has_up; k[15] = n_chunks; k[16] = n_tma_chunks; k[17] = n_ops; k[18] = sms;
+        k[14] = has_up; k[15] = n_chunks; k[16] = n_tma_chunks; k[17] = n_ops; k[18] = sms; k[19] = g_autotune != 0;
     }
     V2Plan plan = {0, 0, 0, 0};
     bool found = false;
@@ -806,7 +890,32 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
             if (e.key == key) { plan = e.plan; found = true; break; }
     }
     if (!found) {
-        plan = search_plan(p, has_up, n_chunks, n_tma_chunks, sms);
+        const std::vector<Candidate> cands = search_plans(p, has_up, n_chunks, n_tma_chunks, sms);
+        KB_CHECK_ARG(!cands.empty(), "conv(v2): no tile fits");
+        plan = cands[0].plan;
+        if (g_autotune && cands.size() > 1) {
+            // Measured tile selection (opt-in: it synchronises the stream the first time a shape is seen): run the cost model's
+            // best candidates on the real tensors -- every candidate writes the same result -- and keep the fastest.
+            cudaEvent_t e0, e1;
+            KB_CUDA(cudaEventCreate(&e0));
+            KB_CUDA(cudaEventCreate(&e1));
+            float best_ms = 1e30f;
+            const size_t n_try = cands.size() < 12 ? cands.size() : 12;
+            for (size_t i = 0; i < n_try; ++i) {
+                int rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);  // warm-up (I-cache, L2)
+                if (rc) continue;
+                KB_CUDA(cudaEventRecord(e0, stream));
+                rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);
+                KB_CUDA(cudaEventRecord(e1, stream));
+                if (rc) continue;
+                KB_CUDA(cudaEventSynchronize(e1));
+                float ms = 0.f;
+                KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                if (ms < best_ms) { best_ms = ms; plan = cands[i].plan; }
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
         if (const char* ov = getenv("KBNET_V2_PLAN")) {  // debugging aid: "R,TW,n_split,dual"
             int a, b, c, d;
             if (sscanf(ov, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) plan = {a, b, c, d};
@@ -814,69 +923,7 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         if (g_plans.size() < 4096) g_plans.push_back({key, plan});
     }
-    KB_CHECK_ARG(plan.R > 0, "conv(v2): no tile fits");
-    long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
-    p.n_raw = 2; p.n_a = 2; p.n_w = 2;
-    // spend the remaining shared memory: weights slots first (cheap), then raw slots, then a third A slot
-    while (p.n_w < V2_MAX_W && p.n_w < 4 && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
-    while (p.n_raw < 4 && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
-    if (p.n_stages > 2 && used + p.a_bytes <= V2_SMEM_LIMIT) { ++p.n_a; used += p.a_bytes; }
-    while (p.n_w < V2_MAX_W && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
-    while (p.n_raw < V2_MAX_RAW && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
-    if (used < 120 * 1024) used = 120 * 1024;  // one CTA per SM (the TMEM budget assumes it)
-
-    V2Maps maps;
-    memset(&maps, 0, sizeof(maps));
-    for (int i = 0; i < n_maps; ++i)
-        KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]]), "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
-
-    const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
-    KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
-    static const int exp_flags = getenv("KBNET_V2_EXP") ? atoi(getenv("KBNET_V2_EXP")) : 0;
-    p.exp = exp_flags;
-    static const char* timeline = getenv("KBNET_V2_TIMELINE");  // debugging aid: dump clock64 stamps of CTA 0 to this file (synchronises!)
-    if (timeline) {
-        KB_CUDA(cudaMalloc(&p.dbg, 6 * 4096 * sizeof(long long)));
-        KB_CUDA(cudaMemsetAsync(p.dbg, 0, 6 * 4096 * sizeof(long long), stream));
-    }
-    static const bool debug = getenv("KBNET_V2_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "[conv v2] geo %d  %dx%dx%d -> %dx%d  stages %d convs %d Npad %d/%d/%d | R %d TW %d P %d MB %d split %d dual %d | tiles %lld grid %lld | "
-                "raw %d x %d B, A %d x %d B, W %d x %d B, smem %lld | tmem %d cols x %d bufs\n",
-                geo, p.N, p.Hin, p.Win, p.Hout, p.Wout, p.n_stages, p.n_convs, p.conv[0].Npad, p.conv[1].Npad, p.conv[2].Npad, p.R, p.TW, p.P, p.MB,
-                p.n_split, p.dual, p.n_tiles, grid, p.n_raw, p.raw_bytes, p.n_a, p.a_bytes, p.n_w, p.w_bytes, used, p.MB * p.cols_block, p.acc_bufs);
-#define V2_LAUNCH(G)                                                                                                          \
-    do {                                                                                                                      \
-        if (p.dual) {                                                                                                         \
-            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));   \
-            conv_v2_kernel<G, true><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                           \
-        } else {                                                                                                              \
-            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));  \
-            conv_v2_kernel<G, false><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                          \
-        }                                                                                                                     \
-    } while (0)
-    if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
-    else if (geo == G_S1K1) V2_LAUNCH(G_S1K1);
-    else if (geo == G_S2K3) V2_LAUNCH(G_S2K3);
-    else V2_LAUNCH(G_S2K1);
-#undef V2_LAUNCH
-    KB_CUDA(cudaGetLastError());
-    count_launch();
-    count_launch_v2();
-    if (timeline) {
-        std::vector<long long> h(6 * 4096);
-        KB_CUDA(cudaStreamSynchronize(stream));
-        KB_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        cudaFree(p.dbg);
-        if (FILE* f = fopen(timeline, "w")) {
-            fprintf(f, "# stages %d chunks_tma_per_tile ? MB %d n_a %d n_raw %d n_w %d acc_bufs %d tiles %lld grid %lld\n", p.n_stages, p.MB, p.n_a, p.n_raw, p.n_w,
-                    p.acc_bufs, p.n_tiles, grid);
-            for (int r = 0; r < 6; ++r)
-                for (int i = 0; i < 4096 && h[r * 4096 + i]; ++i) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
-            fclose(f);
-        }
-    }
-    return 0;
+    return launch_with_plan(p, plan, map_src, n_maps, map_cls, has_up, sms, stream, true);
 }
 
 // same grouping as conv_umma.cu / conv_pack_weights: every source is cut into chunks of <= 8 channels, padded to an even count
@@ -895,6 +942,10 @@ int chunk_list(const int* src_channels, int n_src, int* src_of, int* c0_of, int*
     }
     return g;
 }
+
+}  // namespace
+void set_autotune(int on) { g_autotune = on ? 1 : 0; }
+namespace {
 
 bool v2_disabled() {
     static const bool off = getenv("KBNET_CONV_V1") != nullptr;

@@ -38,6 +38,11 @@ const char* kbnet_last_error(void);
 unsigned long long kbnet_launch_count(void);
 /* ... of which launches of the persistent TMA-fed tcgen05 engine (plain convolutions and fused KB blocks). */
 unsigned long long kbnet_tma_engine_launch_count(void);
+/* Measured tile selection for the tensor-core engine (default off; environment KBNET_AUTOTUNE=1 turns it on as well).
+ * When on, the FIRST call for a new layer shape times the cost model's best tile plans on the caller's tensors (every
+ * candidate writes the same result) and caches the fastest; that first call synchronises `stream`.  Later calls are
+ * asynchronous as usual. */
+void kbnet_set_autotune(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * SparseToDensePool.forward -- replaces reference src/networks.py:2168-2196 (module ctor :2100-2166).

@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import kbnet_b200
 torch.set_grad_enabled(False)
+if os.environ.get('KBNET_AUTOTUNE', '1') != '0':
+    kbnet_b200.set_autotune(True)
 dev = torch.device('cuda:0')
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 lvl = int(sys.argv[2]) if len(sys.argv) > 2 else 2

@@ -8,6 +8,8 @@ from kbnet_b200 import ops, modules
 from bench import synth_inputs, MIN_POOLS, MAX_POOLS, F_IMG, F_DEP, F_DEC
 
 torch.set_grad_enabled(False)
+if os.environ.get('KBNET_AUTOTUNE', '1') != '0':
+    kbnet_b200.set_autotune(True)
 dev = torch.device('cuda:0')
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 model = kbnet_b200.KBNetModel(3, 2, MIN_POOLS, MAX_POOLS, 3, 8, F_IMG, F_DEP, [0, 1, 2, 3], F_DEC, device=dev)
