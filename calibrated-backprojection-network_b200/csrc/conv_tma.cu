@@ -247,23 +247,35 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                         raw = reinterpret_cast<const float*>(sRaw + (size_t)rslot * p.raw_bytes);
                     }
                     // destination of (plane pl, this chunk, entry e): hi at A + ((pl*4 + h) * plane_px + e) * 16, lo two planes further
+                    if (GEO != G_S2K3) {
+                        // single-plane geometries: ALL loads of this thread's items first (the compiler cannot hoist them above the
+                        // operand-plane stores itself: both live in shared memory), then convert and store
+                        float v[MAXI][8];
+#pragma unroll
+                        for (int i = 0; i < MAXI; ++i) {
+                            if (i < n_it && kind == CK_TMA) {
+                                const float* r = raw + (ch.cls ? ro1[i] : ro0[i]);
+                                const int cp = ch.cls ? cp1 : cp0;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) v[i][c] = r[c * cp];
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) v[i][c] = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < MAXI; ++i) {
+                            if (i < n_it) {
+                                uint8_t* d = A + ((size_t)h * p.plane_px + it_e[i]) * 16;
+                                store_split8(d, d + 2 * plane_b, v[i]);
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < MAXI; ++i) {
-                        if (i < n_it && it_e[i] < p.n_entries && !(p.exp & 2)) {
+                        if (GEO == G_S2K3 && i < n_it && it_e[i] < p.n_entries && !(p.exp & 2)) {
                             const int e = it_e[i];
-                            if (GEO == G_S1K3 || GEO == G_S1K1 || GEO == G_S2K1) {
-                                float v[8];
-                                if (kind == CK_TMA) {
-                                    const float* r = raw + (ch.cls ? ro1[i] : ro0[i]);
-                                    const int cp = ch.cls ? cp1 : cp0;
-#pragma unroll
-                                    for (int c = 0; c < 8; ++c) v[c] = r[c * cp];
-                                } else {
-#pragma unroll
-                                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
-                                }
-                                uint8_t* d = A + ((size_t)h * p.plane_px + e) * 16;
-                                store_split8(d, d + 2 * plane_b, v);
+                            if (false) {
                             } else {  // G_S2K3: four parity planes
                                 const int y0 = 2 * (tc.oy0 - 1 + it_ei[i]), x0 = 2 * (tc.ox0 - 1 + it_ej[i]);
                                 if (kind == CK_TMA) {

@@ -113,6 +113,18 @@ __host__ __device__ inline Layout make_layout(int R, int n_pool, int n_conv) {
     return L;
 }
 
+// compile-time helpers for the specialised pool configurations
+__host__ __device__ constexpr int cpopc(unsigned m) { return m ? (int)(m & 1u) + cpopc(m >> 1) : 0; }
+__host__ __device__ constexpr int nth_bit(unsigned m, int k) {  // position of the k-th (0-based) set bit
+    int pos = 0;
+    for (; pos < 32; ++pos)
+        if ((m >> pos) & 1u) {
+            if (k == 0) return pos;
+            --k;
+        }
+    return 0;
+}
+
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
     u64 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -221,13 +233,15 @@ __device__ __forceinline__ void build_weight_image(const WeightSrc& ws, uint8_t*
 __global__ void s2d_pack_weights_kernel(const WeightSrc ws, uint8_t* dst) { build_weight_image(ws, dst, threadIdx.x, blockDim.x); }
 
 // ---- pass 1: vertical nested-window sweep of one tile column segment -----------------------------------------------
-template <int R, bool BORDER>
+// MINM / MAXM >= 0: the pool configuration is a compile-time constant (bit r set <=> a pool of radius r), so every mask test,
+// plane index and radius loop below folds away; -1: taken from the launch parameters (any configuration).
+template <int R, bool BORDER, int MINM, int MAXM>
 __device__ __forceinline__ void pass1(const FastParams& p, const float* s_z, float* s_V, int tid, int gy0, int gx0) {
     constexpr int ZW = PW + 2 * R, ZP = ZW + 4;
     constexpr int NV = LV + 2 * R;
     const float INF = __int_as_float(0x7f800000);
-    const unsigned min_mask = p.ps.min_mask, max_mask = p.ps.max_mask;
-    const int n_min = p.ps.n_min;
+    const unsigned min_mask = MINM >= 0 ? (unsigned)MINM : p.ps.min_mask, max_mask = MAXM >= 0 ? (unsigned)MAXM : p.ps.max_mask;
+    const int n_min = MINM >= 0 ? cpopc((unsigned)(MINM >= 0 ? MINM : 0)) : p.ps.n_min;
     for (int it = tid; it < ZW * (PHV / LV); it += NT) {
         const int seg = it / ZW, j = it - seg * ZW;
         const int rbase = seg * LV;
@@ -305,13 +319,15 @@ __device__ __forceinline__ void hwindow(const float (&v)[LH + 2 * R], int rk, fl
 #undef KB_STEP
 }
 
-template <int R>
+template <int R, int MINM, int MAXM, int NCONV, int CIN>
 __global__ void __launch_bounds__(NT, 2)
 s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_x1) {
     constexpr int ZW = PW + 2 * R, ZH = PHV + 2 * R, ZP = ZW + 4;
+    constexpr bool SPEC = MINM >= 0;  // pool sizes, n_convolution and input_channels are compile-time constants
     extern __shared__ __align__(128) uint8_t smem[];
-    const int np = p.ps.n_pool;
-    const Layout L = make_layout(R, np, p.n_conv);
+    const int np = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) + cpopc((unsigned)(SPEC ? MAXM : 0)) : p.ps.n_pool;
+    const int n_conv = SPEC ? NCONV : p.n_conv;
+    const Layout L = make_layout(R, np, n_conv);
     float* s_w1d = reinterpret_cast<float*>(smem + L.w1d);
     uint2* s_wB = reinterpret_cast<uint2*>(smem + L.wB);
     uint2* s_xc = reinterpret_cast<uint2*>(smem + L.xc);
@@ -332,12 +348,12 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     const int H = p.H, W = p.W;
     const size_t plane = (size_t)H * W;
     const int gy0 = y0 - 1 - R, gx0 = x0 - 2 - R;  // image coordinates of logical z-tile element (0, 0) (smem column 2)
-    const int C_in = p.C_in;
+    const int C_in = SPEC ? CIN : p.C_in;
     const float slope = p.slope;
 
     // ---- A. stage the input tile and the weights ---------------------------------------------------------------------
     const bool bulk_w = p.wpack != nullptr;
-    const uint32_t wbytes = (uint32_t)(w1d_bytes(np, p.n_conv) + WB_BYTES);
+    const uint32_t wbytes = (uint32_t)(w1d_bytes(np, n_conv) + WB_BYTES);
     if (tid == 0 && (p.use_tma || bulk_w)) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -372,8 +388,8 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     // ---- B. pass 1 (vertical) + raw-channel split -------------------------------------------------------------------
     {
         const bool border = gy0 < 0 || gx0 < 0 || gy0 + ZH > H || gx0 + ZW > W;
-        if (border) pass1<R, true>(p, s_z, s_V, tid, gy0, gx0);
-        else        pass1<R, false>(p, s_z, s_V, tid, gy0, gx0);
+        if (border) pass1<R, true, MINM, MAXM>(p, s_z, s_V, tid, gy0, gx0);
+        else        pass1<R, false, MINM, MAXM>(p, s_z, s_V, tid, gy0, gx0);
         // raw channels of the 3x3 conv input as packed bf16: .x = hi pair, .y = lo pair.
         //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
         for (int idx = tid; idx < PH * PW; idx += NT) {
@@ -391,7 +407,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     {
         constexpr int NS = PW / LH;
         const u64 slope2 = pack2(slope, slope);
-        const int n_min = p.ps.n_min;
+        const int n_min = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) : p.ps.n_min;
         for (int s = tid; s < PH * NS; s += NT) {
             const int pr = s / NS, c0 = (s - pr * NS) * LH;
             const int gy = y0 - 1 + pr, gxb = x0 - 2 + c0;
@@ -399,16 +415,16 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             u64 acc[NF][2];
 #pragma unroll
             for (int j = 0; j < NF; ++j) acc[j][0] = acc[j][1] = 0ull;
-            for (int k = 0; k < np; ++k) {
+            // one pool plane: horizontal window -> (999 -> 0) -> optional pyramid output -> first 1x1 layer
+            auto pool_plane = [&](int k, int rk, bool is_min) {
                 const float* src = s_V + (k * PHV + pr) * ZW + c0;
                 float v[LH + 2 * R], m[LH];
-                const int rk = p.ps.radius[k];
 #pragma unroll
                 for (int q = 0; q < (LH + 2 * R) / 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
-                if (k < n_min) {
+                if (is_min) {
                     hwindow<R, true>(v, rk, m);
 #pragma unroll
                     for (int i = 0; i < LH; ++i) m[i] = (m[i] == 999.f) ? 0.f : m[i];
@@ -433,11 +449,21 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
                     acc[2 * jj + 1][0] = ffma2(w2.y, m01, acc[2 * jj + 1][0]);
                     acc[2 * jj + 1][1] = ffma2(w2.y, m23, acc[2 * jj + 1][1]);
                 }
+            };
+            if (SPEC) {
+                constexpr unsigned MM = SPEC ? (unsigned)MINM : 0u, XM = SPEC ? (unsigned)MAXM : 0u;
+                constexpr int NMIN = cpopc(MM), NMAX = cpopc(XM);
+#pragma unroll
+                for (int k = 0; k < NMIN; ++k) pool_plane(k, nth_bit(MM, k), true);
+#pragma unroll
+                for (int k = 0; k < NMAX; ++k) pool_plane(NMIN + k, nth_bit(XM, k), false);
+            } else {
+                for (int k = 0; k < np; ++k) pool_plane(k, p.ps.radius[k], k < n_min);
             }
 #pragma unroll
             for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(acc[j][0], slope2); acc[j][1] = leaky01x2(acc[j][1], slope2); }
 
-            for (int l = 1; l < p.n_conv; ++l) {
+            for (int l = 1; l < n_conv; ++l) {
                 const ulonglong2* wl = reinterpret_cast<const ulonglong2*>(s_w1d + (size_t)(NF * np + (l - 1) * NF * NF) * 2);
                 u64 nxt[NF][2];
 #pragma unroll
@@ -579,7 +605,7 @@ bool make_map(CUtensorMap* tm, const float* x, int NC, int H, int W, int bw, int
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R>
+template <int R, int MINM = -1, int MAXM = -1, int NCONV = 0, int CIN = 0>
 int launch_fast(FastParams& p, cudaStream_t stream) {
     const Layout L = make_layout(R, p.ps.n_pool, p.n_conv);
     alignas(64) CUtensorMap tm_z, tm_x1;
@@ -588,7 +614,7 @@ int launch_fast(FastParams& p, cudaStream_t stream) {
     static const bool no_tma = getenv("KBNET_S2D_NO_TMA") != nullptr;  // debugging aid: stage the tile with plain loads
     p.use_tma = !no_tma && make_map(&tm_z, p.x, p.N * p.C_in, p.H, p.W, PW + 2 * R + 4, PHV + 2 * R) &&
                 (p.C_in == 1 || make_map(&tm_x1, p.x, p.N * p.C_in, p.H, p.W, XP, PH));
-    auto kern = s2d_fused_kernel<R>;
+    auto kern = s2d_fused_kernel<R, MINM, MAXM, NCONV, CIN>;
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     p.tiles_x = cdiv(p.W, TW);
     p.tiles_y = cdiv(p.H, TH);
@@ -704,6 +730,17 @@ int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_si
     p.ws.w3x3 = w_3x3; p.ws.n_conv = n_conv; p.ws.n_pool = p.ps.n_pool; p.ws.C_in = C_in;
     for (int k = 0; k < MAX_POOL; ++k) p.ws.chan[k] = p.ps.chan[k];
     p.n_conv = n_conv; p.wpack = (const uint8_t*)wpack; p.slope = neg_slope;
+    // compile-time specialisations of the shipped configurations (bash/kitti/run_kbnet_kitti_validation.sh:10-16,
+    // bash/void/run_kbnet_void1500.sh:15-16, bash/void/train_kbnet_void1500.sh:21-22); everything else takes the same kernel
+    // with the pool configuration read from the launch parameters
+    static const bool no_spec = getenv("KBNET_S2D_NO_SPEC") != nullptr;
+    const unsigned mm = p.ps.min_mask, xm = p.ps.max_mask;
+    if (!no_spec && n_conv == 3) {
+        if (R == 8 && mm == 0x7Cu && xm == 0x180u && C_in == 2) return launch_fast<8, 0x7C, 0x180, 3, 2>(p, stream);
+        if (R == 8 && mm == 0x7Cu && xm == 0x180u && C_in == 1) return launch_fast<8, 0x7C, 0x180, 3, 1>(p, stream);
+        if (R == 16 && mm == 0x180u && xm == 0x6800u && C_in == 2) return launch_fast<16, 0x180, 0x6800, 3, 2>(p, stream);
+        if (R == 16 && mm == 0x380u && xm == 0x2800u && C_in == 2) return launch_fast<16, 0x380, 0x2800, 3, 2>(p, stream);
+    }
     if (R == 4) return launch_fast<4>(p, stream);
     if (R == 8) return launch_fast<8>(p, stream);
     return launch_fast<16>(p, stream);
