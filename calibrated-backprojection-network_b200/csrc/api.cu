@@ -188,6 +188,26 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
     return conv_launch(p, wpack, (cudaStream_t)stream);
 }
 
+/* nearest-2x upsample + 3x3 conv as four source-resolution 2x2 convolutions (csrc/conv_tma.cu) */
+int kbnet_upconv2x_supported(const float* x, int C, int Hs, int Ws, long long stride_n, int F) {
+    ConvSrcDev s = make_src(x, nullptr, C, Hs, Ws, stride_n, SRC_DIRECT);
+    return upconv2x_supported(s, F) ? 1 : 0;
+}
+
+int kbnet_upconv2x_prepare_weights(const float* w, int F, int C, float* w_parity, void* stream) {
+    return upconv2x_prepare_weights(w, F, C, w_parity, (cudaStream_t)stream);
+}
+
+int kbnet_upconv2x_forward(const float* x, int N, int C, int Hs, int Ws, long long stride_n, const void* const* wpack_parity, int F, int act,
+                           float neg_slope, float* out, long long out_stride_n, void* stream) {
+    if (N == 0) return 0;
+    KB_CHECK_ARG(x && wpack_parity && out && N > 0 && C > 0 && Hs > 0 && Ws > 0 && F > 0, "upconv: bad argument");
+    KB_CHECK_ARG(out_stride_n >= 4LL * F * Hs * Ws && stride_n >= (long long)C * Hs * Ws, "upconv: stride_n too small");
+    ConvSrcDev s = make_src(x, nullptr, C, Hs, Ws, stride_n, SRC_DIRECT);
+    KB_CHECK_ARG(upconv2x_supported(s, F), "upconv: source cannot be described to TMA (W %% 4, alignment) -- use kbnet_conv2d_forward mode 1");
+    return upconv2x_launch(s, N, wpack_parity, F, act, neg_slope, out, out_stride_n, (cudaStream_t)stream);
+}
+
 int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y, float* kinv0, float* kinv1, void* stream) {
     if (N == 0) return 0;
     KB_CHECK_ARG(K && kinv0 && N > 0, "intrinsics_inverse: bad argument");

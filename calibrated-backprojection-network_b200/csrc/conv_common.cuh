@@ -72,6 +72,10 @@ int conv_pack_weights(const float* w, const int* src_channels, int n_src, int F,
 // second-generation engine (conv_tma.cu): persistent, TMA-fed; takes the same packed weights as conv_umma.cu
 bool conv_v2_supported(const ConvParams& p);
 void set_autotune(int on);
+bool upconv2x_supported(const ConvSrcDev& src, int F);
+int upconv2x_prepare_weights(const float* w, int F, int C, float* out4, cudaStream_t stream);
+int upconv2x_launch(const ConvSrcDev& src, int N, const void* const* wpack4, int F, int act, float slope, float* out, long long out_stride_n,
+                    cudaStream_t stream);
 int conv_v2_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
 bool kb_fused_supported(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
                         const float* coordinates, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);

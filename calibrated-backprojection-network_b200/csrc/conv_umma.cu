@@ -119,7 +119,7 @@ size_t conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize) {
 
 int conv_pack_weights(const float* w, const int* src_channels, int n_src, int F, int ksize, void* wpack, cudaStream_t stream) {
     KB_CHECK_ARG(w && wpack && src_channels, "pack: null pointer argument");
-    KB_CHECK_ARG(n_src >= 1 && n_src <= CONV_MAX_SRC && F > 0 && (ksize == 1 || ksize == 3), "pack: bad argument");
+    KB_CHECK_ARG(n_src >= 1 && n_src <= CONV_MAX_SRC && F > 0 && ksize >= 1 && ksize <= 3, "pack: bad argument");
     PackParams p;
     memset(&p, 0, sizeof(p));
     int ng = 0;

@@ -135,7 +135,11 @@ class DecoderBlock(torch.nn.Module):
 
     def forward(self, x, skip, shape, slope):
         size = tuple(skip.shape[-2:]) if skip is not None else tuple(shape)
-        d = _conv([(x, 'up', size)], self.deconv.conv.weight, 1, slope)                   # nearest-up + conv fused
+        d = None
+        if CONV_BACKEND == 'kbnet' and size == (2 * x.shape[-2], 2 * x.shape[-1]):
+            d = ops.upconv2x(x, self.deconv.conv.weight, slope)                           # four 2x2 convs at the source resolution
+        if d is None:
+            d = _conv([(x, 'up', size)], self.deconv.conv.weight, 1, slope)               # nearest-up + conv fused (any ratio)
         srcs = [d, skip] if self.skip_channels > 0 else [d]
         return _conv(srcs, self.conv.weight, 1, slope)                                    # cat([deconv, skip]) fused
 

@@ -57,6 +57,57 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None):
     return out
 
 
+def _upconv_packs(weight):
+    """Four packed parity weights of an up-convolution (cached on the weight tensor like packed_weight)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), 'up2x')
+    cache = weight.__dict__.get('_kbnet_up2x') if hasattr(weight, '__dict__') else None
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    lib = _lib.load()
+    wc = weight.detach().contiguous()
+    f, c = wc.shape[0], wc.shape[1]
+    dev = wc.device
+    wpar = torch.empty((4, f, c, 2, 2), dtype=torch.float32, device=dev)
+    arr = (ctypes.c_int * 1)(c)
+    nbytes = lib.kbnet_conv_wpack_bytes(arr, 1, f, 2)
+    packs = [torch.empty((nbytes,), dtype=torch.uint8, device=dev) for _ in range(4)]
+    with torch.cuda.device(dev):
+        _lib.check(lib.kbnet_upconv2x_prepare_weights(wc.data_ptr(), f, c, wpar.data_ptr(), _stream(dev)), 'kbnet_upconv2x_prepare_weights')
+        for j in range(4):
+            _lib.check(lib.kbnet_conv_pack_weights(wpar[j].data_ptr(), arr, 1, f, 2, packs[j].data_ptr(), _stream(dev)), 'kbnet_conv_pack_weights')
+    try:
+        weight.__dict__['_kbnet_up2x'] = (key, packs)
+    except Exception:
+        pass
+    return packs
+
+
+def upconv2x(x, weight, slope=0.2, out=None):
+    """act(conv3x3(nearest_upsample_2x(x), weight)) as four source-resolution 2x2 convolutions (kbnet_upconv2x_forward);
+    returns None when the tensor-core path cannot take the tensor (caller falls back to conv2d_fused with an 'up' source)."""
+    from .modules import get_precision
+    if get_precision() != 'bf16x3':
+        return None
+    lib = _lib.load()
+    t, sn = _view4('source', x)
+    n, c, hs, ws = t.shape
+    f = weight.shape[0]
+    if tuple(weight.shape[1:]) != (c, 3, 3) or not lib.kbnet_upconv2x_supported(t.data_ptr(), c, hs, ws, sn, f):
+        return None
+    dev = t.device
+    _w(weight, dev)
+    if out is None:
+        out = torch.empty((n, f, 2 * hs, 2 * ws), dtype=torch.float32, device=dev)
+    packs = _upconv_packs(weight)
+    arr = (ctypes.c_void_p * 4)(*[pk.data_ptr() for pk in packs])
+    osn = out.stride(0) if n > 1 else f * 4 * hs * ws
+    with torch.cuda.device(dev):
+        rc = lib.kbnet_upconv2x_forward(t.data_ptr(), n, c, hs, ws, sn, arr, f, 0 if slope is None else 1,
+                                        0.0 if slope is None else float(slope), out.data_ptr(), osn, _stream(dev))
+    _lib.check(rc, 'kbnet_upconv2x_forward')
+    return out
+
+
 def depth_head(x, min_predict_depth, max_predict_depth):
     """min_d / (sigmoid(x) + min_d / max_d)   (reference src/kbnet_model.py:181-184)."""
     lib = _lib.load()

@@ -144,6 +144,18 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
                          int act /* 0 none, 1 leaky */, float neg_slope,
                          float* out, long long out_stride_n, void* stream);
 
+/* Nearest-2x upsample followed by a 3x3 convolution (UpConv2d, reference src/net_utils.py:484-499 with DecoderBlock's
+ * interpolate to exactly twice the size, :1472-1480), computed as FOUR 2x2 convolutions of the source -- one per output
+ * parity, with row/column sums of the 3x3 weights -- on the source grid: 4 taps instead of 9 and no upsampled tensor.
+ *   kbnet_upconv2x_prepare_weights: w [F,C,3,3] -> w_parity [4][F,C,2,2] (parity = 2*py + px);
+ *   pack each w_parity[j] with kbnet_conv_pack_weights(w_parity + j*F*C*4, {C}, 1, F, 2, ...)  (kbnet_conv_wpack_bytes(.., ksize = 2));
+ *   kbnet_upconv2x_forward: x [N,C,Hs,Ws] -> out [N,F,2Hs,2Ws] = act(conv3x3(upsample2x(x), w)).
+ * kbnet_upconv2x_supported() == 0 (W % 4 != 0, unaligned pointer) -> use kbnet_conv2d_forward with a mode-1 source instead. */
+int kbnet_upconv2x_supported(const float* x, int C, int Hs, int Ws, long long stride_n, int F);
+int kbnet_upconv2x_prepare_weights(const float* w, int F, int C, float* w_parity, void* stream);
+int kbnet_upconv2x_forward(const float* x, int N, int C, int Hs, int Ws, long long stride_n, const void* const* wpack_parity, int F,
+                           int act, float neg_slope, float* out, long long out_stride_n, void* stream);
+
 /* K^-1 for the KB layers -- replaces torch.inverse + the scale_intrinsics closure in KBNetEncoder.forward
  * (src/networks.py:317-352): kinv0 = inverse(K), kinv1 = inverse(K * [[sx,1,sx],[1,sy,sy],[1,1,1]]) (may be NULL).
  * K, kinv0, kinv1: [N,9] row-major 3x3 per sample.  One launch instead of ~12 LU / triangular-solve launches per inverse. */

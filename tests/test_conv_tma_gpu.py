@@ -114,3 +114,18 @@ def test_fused_kb_program_vs_oracle(form, dims):
     assert _v2_count() == c0 + 1, 'the KB block did not run as one fused launch'
     for g, r, name in zip(got, ref, ('conv_image', 'conv_depth', 'conv_fused')):
         assert_close(g, r, what='fused KB %s/%s' % (form, name))
+
+
+@pytest.mark.parametrize('shape', [(2, 24, 7, 8, 16), (1, 64, 22, 76, 128), (2, 64, 88, 304, 12), (1, 128, 44, 152, 64), (1, 20, 5, 12, 256)])
+def test_upconv2x_as_four_parity_convs(shape):
+    """nearest-2x upsample + 3x3 conv computed as four 2x2 convolutions at the source resolution (kbnet_upconv2x_forward)"""
+    n, c, h, w, f = shape
+    gen = torch.Generator().manual_seed(41)
+    x = torch.randn(n, c, h, w, generator=gen)
+    wt = torch.randn(f, c, 3, 3, generator=gen) / (9 * c) ** 0.5
+    for slope in (0.2, None):
+        ref = _ref([(x,)], wt, 1, slope, size=(2 * h, 2 * w))
+        c0 = _v2_count()
+        got = kbnet_b200.ops.upconv2x(x.to(DEV), wt.to(DEV), slope)
+        assert got is not None and _v2_count() == c0 + 1
+        assert_close(got, ref, tol=1e-4, what='upconv2x')

@@ -45,6 +45,16 @@ def kb_name(a, kw, y):
 
 
 ops.conv2d_fused = timed(conv_name, ops.conv2d_fused)
+
+
+def up_name(a, kw, y):
+    x, w = a[0], a[1]
+    if y is None:
+        return 'upconv2x (declined)', 0.0
+    return 'upconv2x (4 parity 2x2 convs)  %d -> %d @%dx%d' % (x.shape[1], w.shape[0], y.shape[2], y.shape[3]), 2.0 * y.numel() * w.shape[1] * 9
+
+
+ops.upconv2x = timed(up_name, ops.upconv2x)
 modules.CalibratedBackprojectionBlock.forward = timed(kb_name, modules.CalibratedBackprojectionBlock.forward)
 modules.SparseToDensePool.forward = timed(lambda a, kw, y: ('S2D', 0.0), modules.SparseToDensePool.forward)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
