@@ -71,3 +71,31 @@ def test_batch_slices_equal_full_batch():
     for r in range(2):
         part = m.forward(*kbnet_b200.dist.shard_batch(args, r, 2))
         assert torch.equal(part, full[r:r + 1])
+
+
+@pytest.mark.parametrize('cfg', ['KITTI', 'VOID'])
+def test_full_size_forward_vs_oracle(cfg):
+    """BASELINE configs 3 / 4 at full resolution (one frame): the whole forward -- S2D, four fused KB blocks, decoder with the
+    parity up-convolutions, head -- against the CPU oracle; also with measured tile selection switched on."""
+    c = K.KITTI if cfg == 'KITTI' else K.VOID
+    gen = torch.Generator().manual_seed(5)
+    n = 1
+    image = torch.rand(n, 3, c['h'], c['w'], generator=gen)
+    depth, valid = K.synth_sparse_depth(gen, n, c['h'], c['w'], c['p'], c['dmin'], c['dmax'])
+    k = torch.tensor(c['k']).view(1, 3, 3).repeat(n, 1, 1)
+    n_pool = len(c['min_pools']) + len(c['max_pools'])
+    ws, we, wd = K.make_model_weights(torch.Generator().manual_seed(0), 2, n_pool)
+    ref = K.model_forward(image, depth, valid, k, ws, we, wd, c['min_pools'], c['max_pools'], c['min_pred'], c['max_pred'])
+    m = kbnet_b200.KBNetModel(3, 2, c['min_pools'], c['max_pools'], 3, 8, [48, 96, 192, 384, 384], [16, 32, 64, 128, 128],
+                              [0, 1, 2, 3], [256, 128, 128, 64, 12], min_predict_depth=c['min_pred'],
+                              max_predict_depth=c['max_pred'], device=DEV)
+    m.load_state_dicts(ws, we, wd)
+    args = [t.to(DEV) for t in (image, depth, valid, k)]
+    out = m.forward(*args)
+    assert_close(out, ref, what='%s full-size forward' % cfg)
+    kbnet_b200.set_autotune(True)
+    try:
+        out2 = m.forward(*args)
+    finally:
+        kbnet_b200.set_autotune(False)
+    assert_close(out2, ref, what='%s full-size forward, autotuned tiles' % cfg)
