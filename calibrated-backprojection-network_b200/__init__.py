@@ -5,10 +5,10 @@ Importable as ``kbnet_b200`` (see kbnet_b200.py at the repository root; this dir
 contract asks for).  The compute lives in libkbnet_b200.so (csrc/, C ABI in include/kbnet_b200.h).
 """
 from . import _lib, build as _build, dist, ops
-from .modules import CalibratedBackprojectionBlock, SparseToDensePool, install, set_precision, get_precision
+from .modules import CalibratedBackprojectionBlock, OutlierRemoval, SparseToDensePool, install, set_precision, get_precision
 from .model import KBNetEncoder, KBNetModel, MultiScaleDecoder
 
-__all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
+__all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'OutlierRemoval', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
            'install', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']
 
 

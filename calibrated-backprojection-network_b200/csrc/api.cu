@@ -214,6 +214,14 @@ int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y
     return intrinsics_inverse_launch(K, N, scale_x, scale_y, kinv0, kinv1, (cudaStream_t)stream);
 }
 
+int kbnet_outlier_removal_forward(const float* sparse_depth, const float* validity_map, int N, int H, int W, int kernel_size, float threshold,
+                                  float* out_depth, float* out_validity, void* workspace, void* stream) {
+    if (N == 0) return 0;
+    KB_CHECK_ARG(sparse_depth && out_depth && out_validity && workspace && N > 0 && H > 0 && W > 0, "outlier_removal: bad argument");
+    return outlier_removal_launch(sparse_depth, validity_map, N, H, W, kernel_size, threshold, out_depth, out_validity, workspace,
+                                  (cudaStream_t)stream);
+}
+
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream) {
     KB_CHECK_ARG(x && y && n_elem >= 0, "depth_head: bad argument");
     return depth_head_launch(x, n_elem, min_depth, max_depth, y, (cudaStream_t)stream);

@@ -91,6 +91,8 @@ inline int conv_launch(const ConvParams& p, const void* wpack, cudaStream_t stre
 int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int N, int C, int H, int W, int Ho, int Wo, float slope, float* z,
                      cudaStream_t stream);
 int intrinsics_inverse_launch(const float* K, int N, float sx, float sy, float* kinv0, float* kinv1, cudaStream_t stream);
+int outlier_removal_launch(const float* depth, const float* validity, int N, int H, int W, int ksize, float threshold, float* out_depth,
+                           float* out_valid, void* workspace, cudaStream_t stream);
 int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);
 int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
                 int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack, float neg_slope,

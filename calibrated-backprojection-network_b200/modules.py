@@ -344,6 +344,38 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# OutlierRemoval (pre-processing step immediately before the path)
+# ---------------------------------------------------------------------------------------------------------
+class OutlierRemoval(object):
+    """Mirror of net_utils.OutlierRemoval (reference src/net_utils.py:1745-1806): same constructor and
+    ``remove_outliers(sparse_depth, validity_map)``; ``validity_map=None`` derives it as src/kbnet.py:899-902 does."""
+
+    def __init__(self, kernel_size=7, threshold=1.5):
+        self.kernel_size = kernel_size
+        self.threshold = threshold
+
+    def remove_outliers(self, sparse_depth, validity_map=None):
+        sparse_depth = _check_input('sparse_depth', sparse_depth)
+        n, c, h, w = sparse_depth.shape
+        if c != 1:
+            raise RuntimeError('kbnet_b200: sparse_depth must be [N,1,H,W]')
+        if validity_map is not None:
+            validity_map = _check_input('validity_map', validity_map)
+            if validity_map.shape != sparse_depth.shape:
+                raise RuntimeError('kbnet_b200: validity_map shape %s does not match sparse_depth' % (tuple(validity_map.shape),))
+        dev = sparse_depth.device
+        out_d, out_v = torch.empty_like(sparse_depth), torch.empty_like(sparse_depth)
+        ws = torch.empty((4,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            rc = lib.kbnet_outlier_removal_forward(sparse_depth.data_ptr(), validity_map.data_ptr() if validity_map is not None else None,
+                                                   n, h, w, int(self.kernel_size), float(self.threshold), out_d.data_ptr(), out_v.data_ptr(),
+                                                   ws.data_ptr(), _stream(dev))
+        _lib.check(rc, 'kbnet_outlier_removal_forward')
+        return out_d, out_v
+
+
+# ---------------------------------------------------------------------------------------------------------
 # install(): swap the two classes into the reference's flat modules (SURVEY 8b)
 # ---------------------------------------------------------------------------------------------------------
 def install(networks_module=None, net_utils_module=None):
@@ -356,4 +388,6 @@ def install(networks_module=None, net_utils_module=None):
     originals = (networks_module.SparseToDensePool, net_utils_module.CalibratedBackprojectionBlock)
     networks_module.SparseToDensePool = SparseToDensePool
     net_utils_module.CalibratedBackprojectionBlock = CalibratedBackprojectionBlock
+    if hasattr(net_utils_module, 'OutlierRemoval'):
+        net_utils_module.OutlierRemoval = OutlierRemoval   # src/kbnet.py:134,807 construct it through net_utils
     return originals

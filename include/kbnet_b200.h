@@ -161,6 +161,14 @@ int kbnet_upconv2x_forward(const float* x, int N, int C, int Hs, int Ws, long lo
  * K, kinv0, kinv1: [N,9] row-major 3x3 per sample.  One launch instead of ~12 LU / triangular-solve launches per inverse. */
 int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y, float* kinv0, float* kinv1, void* stream);
 
+/* OutlierRemoval.remove_outliers (reference src/net_utils.py:1761-1806): drop sparse points that are more than `threshold`
+ * behind the nearest point of their kernel_size x kernel_size neighbourhood.  sparse_depth / validity_map / outputs are
+ * [N,1,H,W]; validity_map may be NULL, then it is derived as in src/kbnet.py:899-902 (depth > 0 ? 1 : depth).  The global
+ * maximum the reference reads back to the host stays on the device: `workspace` is >= 4 bytes of device scratch.
+ * kernel_size odd, <= 17.  Bit-exact (selection and comparison only). */
+int kbnet_outlier_removal_forward(const float* sparse_depth, const float* validity_map, int N, int H, int W, int kernel_size,
+                                  float threshold, float* out_depth, float* out_validity, void* workspace, void* stream);
+
 /* Output head of KBNetModel.forward (src/kbnet_model.py:181-184): y = min_d / (sigmoid(x) + min_d / max_d). */
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream);
 

@@ -207,6 +207,20 @@ def make_kb_weights(gen, c_i, c_d, c_fused_in, f_i, f_d, f_f, prefix=''):
     }
 
 
+def outlier_removal(sparse_depth, validity_map=None, kernel_size=7, threshold=1.5):
+    """src/net_utils.py:1761-1806 (and, for validity_map=None, the validity map of src/kbnet.py:899-902)."""
+    if validity_map is None:
+        validity_map = torch.where(sparse_depth > 0, torch.ones_like(sparse_depth), sparse_depth)
+    max_value = 10 * torch.max(sparse_depth)                                          # :1776
+    filled = torch.where(validity_map <= 0, torch.full_like(sparse_depth, float(max_value)), sparse_depth)
+    pad = kernel_size // 2
+    filled = F.pad(filled, (pad, pad, pad, pad), mode='constant', value=float(max_value))   # :1783-1787
+    min_values = -F.max_pool2d(-filled, kernel_size=kernel_size, stride=1, padding=0)      # :1789-1793
+    keep = torch.where(min_values < sparse_depth - threshold, torch.zeros_like(validity_map), torch.ones_like(validity_map))
+    validity_clean = validity_map * keep                                              # :1802
+    return sparse_depth * validity_clean, validity_clean
+
+
 def make_model_weights(gen, c_in_depth=2, n_pool=7, n_filter_s2d=8, n_conv_s2d=3,
                        f_img=(48, 96, 192, 384, 384), f_dep=(16, 32, 64, 128, 128),
                        f_dec=(256, 128, 128, 64, 12)):

@@ -47,6 +47,22 @@ def pyramid_of(s2d, x):
     return out, grabbed['p']
 
 
+def write_outlier_cases(net_utils):
+    gen = torch.Generator().manual_seed(7)
+    cases = []
+    for name, (n, h, w, p, ks, thr) in {'kitti_like': (2, 48, 80, 0.08, 7, 1.5), 'dense_k5': (1, 33, 41, 0.6, 5, 0.5),
+                                        'sparse_k9': (2, 40, 52, 0.01, 9, 2.0), 'empty': (1, 16, 20, 0.0, 7, 1.5)}.items():
+        z = sparse_depth(gen, n, h, w, p)
+        if name == 'kitti_like':                         # plant near/far pairs so that points really get removed, also at borders
+            z[0, 0, 0, 0], z[0, 0, 0, 2] = 5.0, 30.0
+            z[0, 0, 20, 30], z[0, 0, 22, 33] = 4.0, 5.4
+            z[1, 0, 47, 79], z[1, 0, 45, 77] = 60.0, 3.0
+        valid = torch.where(z > 0, torch.ones_like(z), z)
+        d, v = net_utils.OutlierRemoval(kernel_size=ks, threshold=thr).remove_outliers(sparse_depth=z, validity_map=valid)
+        cases.append(dict(name=name, kernel_size=ks, threshold=thr, sparse_depth=z, validity_map=valid, out_depth=d, out_validity=v))
+    torch.save(cases, os.path.join(HERE, 'outlier_cases.pt'))
+
+
 def main():
     networks, net_utils, kbnet_model = import_reference()
     torch.set_grad_enabled(False)
@@ -154,6 +170,8 @@ def main():
                     out_sample=out[:, :, ::16, ::16].clone(), out_absmax=float(out.abs().max()),
                     out_mean=float(out.mean())),
                os.path.join(HERE, 's2d_config1_fullsize.pt'))
+    # ---- OutlierRemoval.remove_outliers (src/net_utils.py:1761-1806) with the validity map of src/kbnet.py:899-902 ----
+    write_outlier_cases(net_utils)
     print('golden fixtures written to', HERE)
     for f in sorted(os.listdir(HERE)):
         print('  %-32s %8d bytes' % (f, os.path.getsize(os.path.join(HERE, f))))

@@ -130,3 +130,14 @@ def test_oracle_vs_live_reference_random_shapes():
     co = K.camera_coordinates(k, 11, 16)
     for a, b in zip(blk(im, de, co, fu), K.kb_forward(im, de, co, fu, blk.state_dict())):
         assert (a - b).abs().max() <= 1e-6
+
+
+@pytest.mark.parametrize('idx', range(4))
+def test_outlier_removal_oracle_matches_reference_fixture(idx):
+    """OutlierRemoval.remove_outliers (src/net_utils.py:1761-1806): the oracle restatement is bit-exact against outputs of
+    the reference itself (tests/golden/make_golden.py::write_outlier_cases)."""
+    c = load_golden('outlier_cases.pt')[idx]
+    d, v = K.outlier_removal(c['sparse_depth'], c['validity_map'], c['kernel_size'], c['threshold'])
+    assert torch.equal(d, c['out_depth']) and torch.equal(v, c['out_validity']), c['name']
+    d2, v2 = K.outlier_removal(c['sparse_depth'], None, c['kernel_size'], c['threshold'])
+    assert torch.equal(d2, c['out_depth']) and torch.equal(v2, c['out_validity'])
