@@ -185,7 +185,21 @@ int kbnet_conv2d_forward(const kbnet_conv_src* srcs, int n_src, int N, int H_in,
     }
     int rc;
     if ((rc = finish_conv(p, N, H_in, W_in, w, F, ksize, stride, act, neg_slope, out, out_stride_n))) return rc;
+    // a handful of filters over a few channels at full resolution: HBM-bound exact-fp32 CUDA-core kernel (conv_small.cu)
+    if (n_src == 1 && srcs[0].mode == 0 && conv_small_supported(srcs[0].C, F, ksize, stride))
+        return conv_small_launch(srcs[0].ptr, srcs[0].stride_n, N, srcs[0].C, H_in, W_in, w, F, act, neg_slope, 0.f, 0.f, out, out_stride_n,
+                                 (cudaStream_t)stream);
     return conv_launch(p, wpack, (cudaStream_t)stream);
+}
+
+int kbnet_conv3x3_depth_head_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, double min_depth,
+                                     double max_depth, float* y, long long y_stride_n, void* stream) {
+    if (N == 0) return 0;
+    KB_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv3x3_depth_head: bad argument");
+    KB_CHECK_ARG(conv_small_supported(C, F, 3, 1), "conv3x3_depth_head: C=%d F=%d unsupported (C <= 32, F <= 4)", C, F);
+    KB_CHECK_ARG(x_stride_n >= (long long)C * H * W && y_stride_n >= (long long)F * H * W, "conv3x3_depth_head: stride_n too small");
+    return conv_small_launch(x, x_stride_n, N, C, H, W, w, F, 2, 0.f, (float)min_depth, (float)(min_depth / max_depth), y, y_stride_n,
+                             (cudaStream_t)stream);
 }
 
 /* nearest-2x upsample + 3x3 conv as four source-resolution 2x2 convolutions (csrc/conv_tma.cu) */

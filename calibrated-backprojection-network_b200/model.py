@@ -163,13 +163,20 @@ class MultiScaleDecoder(torch.nn.Module):
             c = n_filters[i]
         self.output0 = ConvWeight(c, output_channels, 3, 1, weight_initializer)
 
-    def forward(self, x, skips, shape=None):
+    def forward(self, x, skips, shape=None, depth_range=None):
+        """depth_range=(min_d, max_d): return the final DEPTH (output0 fused with the head of kbnet_model.py:181-184)
+        instead of the linear output the reference decoder returns."""
         slope = self.negative_slope
         x = self.deconv4(x, skips[3], None, slope)
         x = self.deconv3(x, skips[2], None, slope)
         x = self.deconv2(x, skips[1], None, slope)
         x = self.deconv1(x, skips[0], None, slope)
         x = self.deconv0(x, None, shape, slope)
+        if depth_range is not None:
+            y = ops.conv3x3_depth_head(x, self.output0.weight, depth_range[0], depth_range[1]) if CONV_BACKEND == 'kbnet' else None
+            if y is None:
+                y = ops.depth_head(_conv([x], self.output0.weight, 1, None), depth_range[0], depth_range[1])
+            return [y]
         return [_conv([x], self.output0.weight, 1, None)]
 
 
@@ -267,7 +274,7 @@ class KBNetModel(object):
         input_depth = self.sparse_to_dense_pool(input_depth)                           # :173
         shape = input_depth.shape[-2:]
         latent, skips = self.encoder(image, input_depth, intrinsics)                   # :177
-        output = self.decoder(latent, skips, shape)[-1]                                # :179
-        return ops.depth_head(output, self.min_predict_depth, self.max_predict_depth)  # :181-184
+        # :179 + :181-184 -- the last convolution and the sigmoid / inverse-depth head are one kernel
+        return self.decoder(latent, skips, shape, depth_range=(self.min_predict_depth, self.max_predict_depth))[-1]
 
     __call__ = forward

@@ -108,6 +108,25 @@ def upconv2x(x, weight, slope=0.2, out=None):
     return out
 
 
+def conv3x3_depth_head(x, weight, min_predict_depth, max_predict_depth):
+    """min_d / (sigmoid(conv3x3(x, weight)) + min_d / max_d): `output0` fused with the head (reference src/networks.py:1989 +
+    src/kbnet_model.py:181-184); None when the layer is not small enough for the fused kernel."""
+    lib = _lib.load()
+    t, sn = _view4('source', x)
+    n, c, h, w_ = t.shape
+    f = weight.shape[0]
+    if tuple(weight.shape[1:]) != (c, 3, 3) or c > 32 or f > 4:
+        return None
+    dev = t.device
+    wt = _w(weight, dev)
+    y = torch.empty((n, f, h, w_), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.kbnet_conv3x3_depth_head_forward(t.data_ptr(), sn, n, c, h, w_, wt.data_ptr(), f, float(min_predict_depth),
+                                                  float(max_predict_depth), y.data_ptr(), f * h * w_, _stream(dev))
+    _lib.check(rc, 'kbnet_conv3x3_depth_head_forward')
+    return y
+
+
 def depth_head(x, min_predict_depth, max_predict_depth):
     """min_d / (sigmoid(x) + min_d / max_d)   (reference src/kbnet_model.py:181-184)."""
     lib = _lib.load()

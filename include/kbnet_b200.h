@@ -161,6 +161,12 @@ int kbnet_upconv2x_forward(const float* x, int N, int C, int Hs, int Ws, long lo
  * K, kinv0, kinv1: [N,9] row-major 3x3 per sample.  One launch instead of ~12 LU / triangular-solve launches per inverse. */
 int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y, float* kinv0, float* kinv1, void* stream);
 
+/* The last decoder convolution fused with the output head: y = min_d / (sigmoid(conv3x3_pad1(x, w)) + min_d / max_d)
+ * (`output0`, a linear-output Conv2d, reference src/networks.py:1855-1989, followed by src/kbnet_model.py:181-184).
+ * x [N,C,H,W] (C <= 32), w [F,C,3,3] (F <= 4), y [N,F,H,W]; exact fp32 on the CUDA cores -- the layer is HBM-bound. */
+int kbnet_conv3x3_depth_head_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F,
+                                     double min_depth, double max_depth, float* y, long long y_stride_n, void* stream);
+
 /* OutlierRemoval.remove_outliers (reference src/net_utils.py:1761-1806): drop sparse points that are more than `threshold`
  * behind the nearest point of their kernel_size x kernel_size neighbourhood.  sparse_depth / validity_map / outputs are
  * [N,1,H,W]; validity_map may be NULL, then it is derived as in src/kbnet.py:899-902 (depth > 0 ? 1 : depth).  The global

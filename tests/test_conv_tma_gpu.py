@@ -35,10 +35,10 @@ CASES = [
     ('s1_wide', 1, [8], 16, 300, 16, 3, 1),
     ('s1_two_src', 2, [20, 13], 19, 36, 24, 3, 1),
     ('s1_f12', 1, [64], 24, 40, 12, 3, 1),
-    ('s1_f1', 1, [12], 21, 32, 1, 3, 1),
     ('s1_c200_f256', 1, [200], 11, 40, 256, 3, 1),
     ('s1_many_tiles', 2, [32, 32], 88, 304, 64, 3, 1),
     ('s1_fullres_f12', 1, [12], 352, 1216, 12, 3, 1),
+    ('s1_c40_f1', 1, [40], 21, 32, 1, 3, 1),
     ('s2_small', 1, [16], 12, 20, 16, 3, 2),
     ('s2_odd_h', 2, [19], 13, 20, 32, 3, 2),
     ('s2_c48_f96', 2, [48], 44, 76, 96, 3, 2),

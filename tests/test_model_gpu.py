@@ -99,3 +99,22 @@ def test_full_size_forward_vs_oracle(cfg):
     finally:
         kbnet_b200.set_autotune(False)
     assert_close(out2, ref, what='%s full-size forward, autotuned tiles' % cfg)
+
+
+@pytest.mark.parametrize('shape', [(2, 12, 21, 33, 1), (1, 12, 352, 1216, 1), (2, 7, 16, 130, 3), (1, 32, 9, 64, 4)])
+def test_small_direct_conv_and_fused_depth_head(shape):
+    """conv_small.cu: exact-fp32 direct 3x3 convolution for <= 4 filters (KBNet's output0), alone and fused with the depth head"""
+    import torch.nn.functional as F
+    n, c, h, w, f = shape
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(n, c, h, w, generator=gen)
+    wt = torch.randn(f, c, 3, 3, generator=gen) * 0.2
+    ref = F.conv2d(x.double(), wt.double(), padding=1).float()
+    lib = kbnet_b200._lib.load()
+    c0 = lib.kbnet_tma_engine_launch_count()
+    got = kbnet_b200.ops.conv2d_fused([x.to(DEV)], wt.to(DEV), 1, None)
+    assert lib.kbnet_tma_engine_launch_count() == c0, 'expected the CUDA-core kernel for a <= 4-filter layer'
+    assert_close(got, ref, tol=1e-5, what='small conv, linear')
+    assert_close(kbnet_b200.ops.conv2d_fused([x.to(DEV)], wt.to(DEV), 1, 0.2), F.leaky_relu(ref, 0.2), tol=1e-5, what='small conv, leaky')
+    head = kbnet_b200.ops.conv3x3_depth_head(x.to(DEV), wt.to(DEV), 1.5, 100.0)
+    assert_close(head, 1.5 / (torch.sigmoid(ref) + 1.5 / 100.0), tol=1e-5, what='fused depth head')
