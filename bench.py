@@ -56,15 +56,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe): NVML every ~5 ms when
+    nvidia_ml_py is importable (a bench step is a few ms), else nvidia-smi polling."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            bits = (('hw_slowdown', n.nvmlClocksThrottleReasonHwSlowdown), ('hw_thermal_slowdown', n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ('sw_thermal_slowdown', n.nvmlClocksThrottleReasonSwThermalSlowdown), ('sw_power_cap', n.nvmlClocksThrottleReasonSwPowerCap))
+            try:
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            while not self.stop_flag:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                    self.rows.append([str(sm), str(mx), str(pw)] + ['Active' if rs & b else 'Not Active' for _, b in bits])
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
@@ -85,7 +119,9 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()), default=None)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(self.rows)}
+        pw = max((float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(self.rows),
+                'power_w_max': pw, 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_forward_fn():
@@ -131,7 +167,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='kbnet', choices=['kbnet', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='frames per GPU per step')

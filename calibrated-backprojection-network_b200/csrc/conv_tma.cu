@@ -146,10 +146,17 @@ struct Ring {
     }
 };
 
+// clock64 stamps of CTA 0 for tools/v2_timeline.py: compiled in only with -DKBNET_V2_STAMPS (they sit in the hot loops of every role)
+#ifdef KBNET_V2_STAMPS
 #define V2_STAMP(role, idx)                                                                             \
     do {                                                                                                  \
         if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 4096) p.dbg[(role) * 4096 + (idx)] = clock64(); \
     } while (0)
+#else
+#define V2_STAMP(role, idx) \
+    do {                    \
+    } while (0)
+#endif
 
 struct TileCoord {
     int n, oy0, ox0, split;
@@ -463,8 +470,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         constexpr bool dual = DUAL;
         // operand-plane offset (in 16-byte rows) of tap t: a 3x3 tap is the same plane read from a shifted start address
         const uint32_t P_u = (uint32_t)p.P, plane4 = 4u * (uint32_t)p.plane_px;
-        auto tap_offset = [&](uint32_t t) -> uint32_t {
-            const uint32_t ky = (t * 11u) >> 5, kx = t - 3u * ky;  // t / 3, t % 3 for t < 9
+        auto tap_offset = [&](uint32_t ky, uint32_t kx) -> uint32_t {
             if (GEO == G_S1K3) return ky * P_u + kx;  // (tap 4 = the centre: P + 1)
             if (GEO == G_S2K3)  // dy = ky - 1, dx = kx - 1: parity plane (dy != 0, dx != 0), shift (dy >= 0) * P + (dx >= 0)
                 return ((ky != 1u ? 2u : 0u) + (kx != 1u ? 1u : 0u)) * plane4 + (ky != 0u ? P_u : 0u) + (kx != 0u ? 1u : 0u);
@@ -496,13 +502,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                             uint32_t a0 = a_base16 + off;
                             uint32_t d = dcol;
                             if (dual) {  // B' = [b_hi | b_lo] interleaved per 8-filter group (SBO 256 B): all four hi/lo products in two MMAs
-#pragma unroll 2
+#pragma unroll 1
                                 for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
                                     mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi256), idesc2, accum);
                                     mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi256), idesc2, 1u);
                                 }
                             } else {
-#pragma unroll 2
+#pragma unroll 1
                                 for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
                                     mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi512), idesc1, accum);
                                     mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi512), idesc1, 1u);
@@ -516,24 +522,28 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                             const int Tu = left < p.T ? left : p.T;  // taps per weight-ring slot
                             int cnt = 0;
                             uint32_t b16 = 0, accum = us.first ? 0u : 1u;
+#pragma unroll 1
+                            for (uint32_t ky = 0; ky < 3; ++ky) {  // rows rolled, columns unrolled: a third of the code of a full unroll
 #pragma unroll
-                            for (uint32_t t = 0; t < 9; ++t) {  // unrolled: constant tap offsets stay in uniform registers (a rolled loop costs ~60 dependent instructions per tap)
-                                if (!((mask >> t) & 1u)) continue;
-                                if (cnt == 0) {
-                                    V2_STAMP(5, dbg_w); ++dbg_w;
-                                    mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
-                                    V2_STAMP(5, dbg_w); ++dbg_w;
-                                    b16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
-                                }
-                                do_tap(tap_offset(t), b16, accum);
-                                accum = 1u;
-                                b16 += piece16;
-                                --left;
-                                if (++cnt == Tu || left == 0) {
-                                    mma_commit(BAR(B_W_EMPTY + w_r.slot));
-                                    V2_STAMP(5, dbg_w); ++dbg_w;
-                                    w_r.advance(n_w);
-                                    cnt = 0;
+                                for (uint32_t kx = 0; kx < 3; ++kx) {
+                                    const uint32_t t = 3u * ky + kx;
+                                    if (!((mask >> t) & 1u)) continue;
+                                    if (cnt == 0) {
+                                        V2_STAMP(5, dbg_w); ++dbg_w;
+                                        mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
+                                        V2_STAMP(5, dbg_w); ++dbg_w;
+                                        b16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
+                                    }
+                                    do_tap(tap_offset(ky, kx), b16, accum);
+                                    accum = 1u;
+                                    b16 += piece16;
+                                    --left;
+                                    if (++cnt == Tu || left == 0) {
+                                        mma_commit(BAR(B_W_EMPTY + w_r.slot));
+                                        V2_STAMP(5, dbg_w); ++dbg_w;
+                                        w_r.advance(n_w);
+                                        cnt = 0;
+                                    }
                                 }
                             }
                         }
@@ -922,14 +932,19 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
             for (size_t i = 0; i < n_try; ++i) {
                 int rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);  // warm-up (I-cache, L2)
                 if (rc) continue;
-                KB_CUDA(cudaEventRecord(e0, stream));
-                rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);
-                KB_CUDA(cudaEventRecord(e1, stream));
+                float cand_ms = 1e30f;
+                for (int rep = 0; rep < 3 && !rc; ++rep) {  // best of three: a single shot is too noisy to rank close candidates
+                    KB_CUDA(cudaEventRecord(e0, stream));
+                    rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);
+                    KB_CUDA(cudaEventRecord(e1, stream));
+                    if (rc) break;
+                    KB_CUDA(cudaEventSynchronize(e1));
+                    float ms = 0.f;
+                    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                    cand_ms = ms < cand_ms ? ms : cand_ms;
+                }
                 if (rc) continue;
-                KB_CUDA(cudaEventSynchronize(e1));
-                float ms = 0.f;
-                KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-                if (ms < best_ms) { best_ms = ms; plan = cands[i].plan; }
+                if (cand_ms < best_ms) { best_ms = cand_ms; plan = cands[i].plan; }
             }
             cudaEventDestroy(e0);
             cudaEventDestroy(e1);
