@@ -20,7 +20,7 @@ convs)
 probe)
   timeout 120 tools/bin/pipe_probe > gpurun_out/pipe_probe.log 2>&1; cat gpurun_out/pipe_probe.log;;
 launches)
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1;;
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune > gpurun_out/bench_ncu.log 2>&1;;
 ncu_s2d)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2d_fused -s 3 -c 1 -o gpurun_out/prof_s2d -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_s2d.log 2>&1
   ncu -i gpurun_out/prof_s2d.ncu-rep --page raw --csv > gpurun_out/prof_s2d_raw.csv 2>/dev/null;;
