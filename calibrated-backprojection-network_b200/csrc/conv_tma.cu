@@ -29,6 +29,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -100,7 +101,6 @@ struct V2Params {
     const float* kinv;    // [N, 9]   (CK_COORDS / CK_XYZ)
     const float* w_proj;  // [C_z]    (zacc)
     int C_z;
-    int exp;              // experiment switches (KBNET_V2_EXP), 0 in production
     long long* dbg;       // optional timeline buffer (KBNET_V2_TIMELINE): [role 0..4][4096] clock64 stamps of CTA 0
 };
 struct alignas(64) V2Maps {
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                     }
 #pragma unroll
                     for (int i = 0; i < MAXI; ++i) {
-                        if (GEO == G_S2K3 && i < n_it && it_e[i] < p.n_entries && !(p.exp & 2)) {
+                        if (GEO == G_S2K3 && i < n_it && it_e[i] < p.n_entries) {
                             const int e = it_e[i];
                             if (false) {
                             } else {  // G_S2K3: four parity planes
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             if (tid == 12 * 32) { V2_STAMP(3, dbg_i); ++dbg_i; }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * tile_cols + ((uint32_t)(quarter * 32) << 16);
-            for (int mb = 0; mb < ((p.exp & 4) ? 0 : p.MB); ++mb) {
+            for (int mb = 0; mb < p.MB; ++mb) {
                 const int q = mb * 128 + quarter * 32 + lane;
                 const int oyl = q / p.P, oxl = q - oyl * p.P;
                 const int oy = tc.oy0 + oyl, ox = tc.ox0 + oxl;
@@ -722,7 +722,8 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     p.raw_bytes = roundup(raw0 > raw1 ? raw0 : raw1, 128);
     p.a_bytes = roundup(p.n_planes * 4 * p.plane_px * 16, 128);
     // weight-ring slot: as many taps of a 3x3 use as fit ~24 KB (one barrier round trip and one bulk copy per slot)
-    p.T = max_nsl * 64 * 9 <= 24 * 1024 ? 9 : (max_nsl * 64 * 4 <= 24 * 1024 ? 4 : (max_nsl * 64 * 3 <= 24 * 1024 ? 3 : 1));
+    const int wcap = 24 * 1024;
+    p.T = max_nsl * 64 * 9 <= wcap ? 9 : (max_nsl * 64 * 4 <= wcap ? 4 : (max_nsl * 64 * 3 <= wcap ? 3 : 1));
     int max_taps = 1;
     for (int j = 0; j < p.n_convs; ++j) max_taps = p.conv[j].ntaps > max_taps ? p.conv[j].ntaps : max_taps;
     if (p.T > max_taps) p.T = max_taps;
@@ -809,7 +810,7 @@ std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks
     return cands;
 }
 
-int g_autotune = -1;  // -1: not initialised (KBNET_AUTOTUNE), 0 off, 1 on
+std::atomic<int> g_autotune{-1};  // -1: not initialised (KBNET_AUTOTUNE), 0 off, 1 on
 
 // geometry + rings + tensor maps + launch for one plan
 int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, int sms,
@@ -818,12 +819,19 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
     KB_CHECK_ARG(used > 0 && used <= V2_SMEM_LIMIT, "conv(v2): plan R=%d TW=%d split=%d dual=%d does not fit", plan.R, plan.TW, plan.n_split, plan.dual);
     p.n_raw = 2; p.n_a = 2; p.n_w = 2;
-    // spend the remaining shared memory: weights slots first (cheap), then raw slots, then a third A slot
-    while (p.n_w < V2_MAX_W && p.n_w < 4 && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
-    while (p.n_raw < 4 && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
-    if (p.n_stages > 2 && used + p.a_bytes <= V2_SMEM_LIMIT) { ++p.n_a; used += p.a_bytes; }
-    while (p.n_w < V2_MAX_W && used + p.w_bytes <= V2_SMEM_LIMIT) { ++p.n_w; used += p.w_bytes; }
-    while (p.n_raw < V2_MAX_RAW && used + p.raw_bytes <= V2_SMEM_LIMIT) { ++p.n_raw; used += p.raw_bytes; }
+    // Spend the remaining shared memory on ring depth, in the order in which exposed latency was measured to cost (role timelines,
+    // tools/v2_timeline.py): a raw slot is refilled only after the converters release it, so with 2 slots every chunk waits a full
+    // TMA round trip (~2 k clk); weights and a third operand stage come next.
+    auto grow = [&](int& n, int bytes, int upto) {
+        while (n < upto && used + bytes <= V2_SMEM_LIMIT) { ++n; used += bytes; }
+    };
+    grow(p.n_raw, p.raw_bytes, 3);
+    grow(p.n_w, p.w_bytes, 3);
+    grow(p.n_raw, p.raw_bytes, 4);
+    if (p.n_stages > 2) grow(p.n_a, p.a_bytes, 3);
+    grow(p.n_w, p.w_bytes, 4);
+    grow(p.n_raw, p.raw_bytes, V2_MAX_RAW);
+    grow(p.n_w, p.w_bytes, V2_MAX_W);
     if (used < 120 * 1024) used = 120 * 1024;  // one CTA per SM (the TMEM budget assumes it)
 
     V2Maps maps;
@@ -833,8 +841,6 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
 
     const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
     KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
-    static const int exp_flags = getenv("KBNET_V2_EXP") ? atoi(getenv("KBNET_V2_EXP")) : 0;
-    p.exp = exp_flags;
     static const char* timeline = getenv("KBNET_V2_TIMELINE");  // debugging aid: dump clock64 stamps of CTA 0 to this file (synchronises!)
     p.dbg = nullptr;
     if (timeline && report) {
@@ -901,14 +907,15 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
             if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
         }
     }
-    if (g_autotune < 0) g_autotune = getenv("KBNET_AUTOTUNE") ? atoi(getenv("KBNET_AUTOTUNE")) : 0;
+    if (g_autotune.load() < 0) g_autotune.store(getenv("KBNET_AUTOTUNE") ? (atoi(getenv("KBNET_AUTOTUNE")) != 0) : 0);
+    const int autotune = g_autotune.load();
     PlanKey key;
     memset(&key, 0, sizeof(key));
     {
         int* k = key.v;
         k[0] = geo; k[1] = p.N; k[2] = p.Hin; k[3] = p.Win; k[4] = p.Hout; k[5] = p.Wout; k[6] = p.n_stages; k[7] = p.n_convs;
         for (int j = 0; j < p.n_convs; ++j) { k[8 + j] = p.conv[j].Npad; k[12 + j] = p.conv[j].ntaps; }
-        k[16] = has_up; k[17] = n_chunks; k[18] = n_tma_chunks; k[19] = n_ops; k[20] = sms; k[21] = g_autotune != 0;
+        k[16] = has_up; k[17] = n_chunks; k[18] = n_tma_chunks; k[19] = n_ops; k[20] = sms; k[21] = autotune != 0;
     }
     V2Plan plan = {0, 0, 0, 0};
     bool found = false;
@@ -921,7 +928,7 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
         const std::vector<Candidate> cands = search_plans(p, has_up, n_chunks, n_tma_chunks, sms);
         KB_CHECK_ARG(!cands.empty(), "conv(v2): no tile fits");
         plan = cands[0].plan;
-        if (g_autotune && cands.size() > 1) {
+        if (autotune && cands.size() > 1) {
             // Measured tile selection (opt-in: it synchronises the stream the first time a shape is seen): run the cost model's
             // best candidates on the real tensors -- every candidate writes the same result -- and keep the fastest.
             cudaEvent_t e0, e1;
@@ -977,7 +984,7 @@ int chunk_list(const int* src_channels, int n_src, int* src_of, int* c0_of, int*
 }
 
 }  // namespace
-void set_autotune(int on) { g_autotune = on ? 1 : 0; }
+void set_autotune(int on) { g_autotune.store(on ? 1 : 0); }
 namespace {
 
 bool v2_disabled() {
