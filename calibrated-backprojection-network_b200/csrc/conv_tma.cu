@@ -579,54 +579,52 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                 const bool valid = oyl < p.R && oxl < p.TW && oy < p.Hout && ox < p.Wout;
                 for (int j = 0; j < p.n_convs; ++j) {
                     const V2Conv& cv = p.conv[j];
-                    const size_t oplane = (size_t)cv.oplane;
                     const int f0 = tc.split * cv.Nsl;
                     const int nf = cv.F - f0 < cv.Nsl ? cv.F - f0 : cv.Nsl;  // real filters of this split part (may be <= 0)
+                    if (nf <= 0) continue;
+                    // warp-uniform 64-bit base + per-thread 32-bit element offset (one sample's output is far below 2^32 elements):
+                    // one IMAD.WIDE per store instead of a 64-bit multiply-add chain
+                    // running pointer: one 64-bit add per store instead of a multiply-add chain per filter plane
+                    const size_t oplane = (size_t)cv.oplane;
                     float* dst = cv.out + (size_t)tc.n * cv.out_stride_n + (size_t)f0 * oplane + (size_t)cv.o_off + (size_t)oy * cv.o_row_pitch +
                                  (size_t)ox * cv.o_col_mul;
                     const uint32_t tcol = acc + (uint32_t)(mb * p.cols_block + cv.col);
                     const bool act = cv.act != 0;
-                    if (nf <= 0) continue;
-                    // batches of 16 filters; the TMEM load of batch b+1 is in flight while batch b is activated and stored
-                    uint32_t r0[16], r1[16];
-                    if (DUAL) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
-                        tmem_ld_x16(tcol, r0);
-                        tmem_ld_x16(tcol + 16u, r1);
-                    } else {
-                        tmem_ld_x16(tcol, r0);
-                    }
-                    for (int c = 0; c < nf; c += 16, dst += 16 * oplane) {
+                    for (int c = 0; c < nf; c += 16) {
                         float o[16];
-                        tmem_ld_wait();
-                        if (DUAL) {
+                        if (DUAL) {  // filter 8g + j lives in columns 16g + j (b_hi products) and 16g + 8 + j (b_lo products)
+                            uint32_t r0[16], r1[16];
+                            tmem_ld_x16(tcol + (uint32_t)(2 * c), r0);
+                            tmem_ld_x16(tcol + (uint32_t)(2 * c + 16), r1);
+                            tmem_ld_wait();
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 o[k] = __uint_as_float(r0[k]) + __uint_as_float(r0[k + 8]);
                                 o[k + 8] = __uint_as_float(r1[k]) + __uint_as_float(r1[k + 8]);
                             }
-                            if (c + 16 < nf) {
-                                tmem_ld_x16(tcol + (uint32_t)(2 * c + 32), r0);
-                                tmem_ld_x16(tcol + (uint32_t)(2 * c + 48), r1);
-                            }
                         } else {
+                            uint32_t r0[16];
+                            tmem_ld_x16(tcol + (uint32_t)c, r0);
+                            tmem_ld_wait();
 #pragma unroll
                             for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(r0[k]);
-                            if (c + 16 < nf) tmem_ld_x16(tcol + (uint32_t)(c + 16), r0);
                         }
                         if (act) {
 #pragma unroll
                             for (int k = 0; k < 16; ++k) o[k] = leaky(o[k], p.slope);
                         }
                         if (valid) {
+                            float* d = dst;
                             if (c + 16 <= nf) {
 #pragma unroll
-                                for (int k = 0; k < 16; ++k) dst[(size_t)k * oplane] = o[k];
+                                for (int k = 0; k < 16; ++k, d += oplane) *d = o[k];
                             } else {
 #pragma unroll
-                                for (int k = 0; k < 16; ++k)
-                                    if (c + k < nf) dst[(size_t)k * oplane] = o[k];
+                                for (int k = 0; k < 16; ++k, d += oplane)
+                                    if (c + k < nf) *d = o[k];
                             }
                         }
+                        dst += 16 * oplane;
                     }
                 }
             }
