@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             it_ei[i] = ei; it_ej[i] = ej;
             if (GEO == G_S1K3) { ro0[i] = ei * p.BW[0] + ej + 3; ro1[i] = ((ei + 1) >> 1) * p.BW[1] + ((ej + 1) >> 1) + 3; }
             else if (GEO == G_S1K1) { ro0[i] = ei * p.BW[0] + ej; ro1[i] = 0; }
-            else if (GEO == G_S2K3) { ro0[i] = (2 * ei) * p.BW[0] + 2 * ej + 2; ro1[i] = 0; }
+            else if (GEO == G_S2K3) { ro0[i] = (2 * ei) * p.BW[0] + 2 * ej + 2; ro1[i] = ei * p.BW[1] + 2 * ej + 2; }
             else { ro0[i] = (2 * ei) * p.BW[0] + 2 * ej; ro1[i] = 0; }
             if (e < p.n_entries) n_it = i + 1;
         }
@@ -332,9 +332,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
 #pragma unroll
                                     for (int c = 0; c < 8; ++c) v[c] = 0.f;
                                     if (kind == CK_TMA_P0) {
-                                        const float* r = raw + ro0[i];
+                                        const float* r = raw + (ch.cls ? ro1[i] : ro0[i]);
+                                        const int cp = ch.cls ? cp1 : cp0;
 #pragma unroll
-                                        for (int c = 0; c < 8; ++c) v[c] = r[c * cp0];
+                                        for (int c = 0; c < 8; ++c) v[c] = r[c * cp];
                                     } else if (kind == CK_XYZ || kind == CK_XYZ_T) {
                                         const float z = leaky(zacc[i], p.slope);
                                         const bool in = (unsigned)y0 < (unsigned)p.Hin && (unsigned)x0 < (unsigned)p.Win;
@@ -393,7 +394,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                 else if (GEO == G_S1K1) { x0c = tc.ox0; y0c = tc.oy0; }
                 else if (GEO == G_S2K3) { x0c = 2 * tc.ox0 - 4; y0c = 2 * tc.oy0 - 2; }
                 else { x0c = 2 * tc.ox0; y0c = 2 * tc.oy0; }
-                const int x1c = (tc.ox0 >> 1) - 4, y1c = (tc.oy0 >> 1) - 1;  // half-resolution sources (G_S1K3 only)
+                // class 1: half-resolution sources (G_S1K3) / even-row boxes of the stride-2 programs (same origin as class 0)
+                const int x1c = GEO == G_S2K3 ? x0c : (tc.ox0 >> 1) - 4, y1c = GEO == G_S2K3 ? y0c : (tc.oy0 >> 1) - 1;
                 for (int s = 0; s < p.n_stages; ++s) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -665,13 +667,14 @@ bool tma_ok(const ConvSrcDev& s) {
     return s.ptr != nullptr && ((uintptr_t)s.ptr & 15) == 0 && (s.W & 3) == 0 && (s.stride_n & 3) == 0 && s.W >= 4;
 }
 
-bool make_map4(CUtensorMap* tm, const ConvSrcDev& s, int N, int bw, int bh) {
+// row_step = 2: the box visits every other row (TMA traversal stride): bh rows are LOADED, spanning 2 * bh source rows
+bool make_map4(CUtensorMap* tm, const ConvSrcDev& s, int N, int bw, int bh, int row_step = 1) {
     EncodeTiledFn enc = encode_fn();
-    if (!enc || bw > 256 || bh > 256 || bw < 1 || bh < 1) return false;
+    if (!enc || bw > 256 || bh * row_step > 256 || bw < 1 || bh < 1) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.C, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)s.W * 4, (cuuint64_t)s.W * s.H * 4, (cuuint64_t)s.stride_n * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, 8, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)(bh * row_step), 8, 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)row_step, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(s.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -696,6 +699,7 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     else { p.P = TW; p.n_entries = R * p.P; max_shift = 0; p.BW[0] = 2 * TW; p.BH[0] = 2 * R; }
     p.BW[1] = p.BH[1] = 4;
     if (has_up) { p.BW[1] = roundup(TW / 2 + 5, 4); p.BH[1] = R / 2 + 2; }
+    if (geo == G_S2K3) { p.BW[1] = p.BW[0]; p.BH[1] = R + 1; }  // class 1 of the stride-2 programs: even rows only (sources read at even pixels)
     p.n_planes = geo == G_S2K3 ? 4 : 1;
     p.MB = cdiv(R * p.P, 128);
     const int max_entries = (geo == G_S2K3 || geo == G_S2K1) ? 2 * V2_CONV_THREADS : 4 * V2_CONV_THREADS;
@@ -835,7 +839,8 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     V2Maps maps;
     memset(&maps, 0, sizeof(maps));
     for (int i = 0; i < n_maps; ++i)
-        KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]]), "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
+        KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]], (geo == G_S2K3 && map_cls[i] == 1) ? 2 : 1),
+                     "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
 
     const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
     KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
@@ -1097,7 +1102,7 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
     srcs[1] = mk(depth, C_d, depth_sn);
     srcs[2] = fused ? mk(fused, C_f, fused_sn) : srcs[0];
     srcs[3] = coordinates ? mk(coordinates, 3, 3LL * H * W) : srcs[0];
-    const uint8_t map_cls[V2_MAX_MAPS] = {0, 0, 0, 0};
+    const uint8_t map_cls[V2_MAX_MAPS] = {0, 0, 1, 0};  // `fused` is only read at even pixels: even-row boxes (half the traffic)
     int s = 0;
     // (1) depth chunks -> conv_depth (9 taps) and the z projection
     for (int j = 0; j < C_d / 16; ++j, ++s) {
@@ -1136,7 +1141,7 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
                     if (coordinates) { ch.kind = CK_XYZ_T; ch.tmap = 3; ch.nch = 3; ch.c0 = 0; }
                     else ch.kind = CK_XYZ;
                 } else if (k < n_rest) {
-                    ch.kind = CK_TMA_P0; ch.tmap = 2; ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1));
+                    ch.kind = CK_TMA_P0; ch.tmap = 2; ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1)); ch.cls = 1;
                 } else {
                     ch.kind = CK_NONE;
                 }
