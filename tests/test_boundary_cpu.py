@@ -45,6 +45,21 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert rc != 0 and b'null' in lib.kbnet_last_error()
     with pytest.raises(RuntimeError, match='kbnet_b200 .* failed'):
         _lib.check(rc, 'kbnet_s2d_forward')
+    # the entry points added around the path: invalid arguments are rejected before any CUDA call
+    BADARG = 10001
+    assert lib.kbnet_upconv2x_forward(None, 1, 8, 4, 4, 128, None, 8, 1, 0.2, None, 512, None) == BADARG
+    assert lib.kbnet_outlier_removal_forward(None, None, 1, 8, 8, 7, 1.5, None, None, None, None) == BADARG
+    assert b'outlier_removal' in lib.kbnet_last_error()
+    assert lib.kbnet_conv3x3_depth_head_forward(None, 0, 1, 12, 8, 8, None, 1, 1.5, 100.0, None, 0, None) == BADARG
+    assert lib.kbnet_conv2d_forward(None, 1, 1, 8, 8, None, None, 8, 3, 1, 1, 0.2, None, 512, None) == BADARG
+    assert lib.kbnet_kb_forward(None, 0, None, 0, None, 0, None, None, 1, 16, 16, 0, 8, 8, None, 16, None, 16, None, None, 16, None, None, None,
+                                0.2, None, 0, None, 0, None, 0, None, 0, None) == BADARG
+    assert lib.kbnet_intrinsics_inverse(None, 1, 0.5, 0.5, None, None, None) == BADARG
+    # empty batches are a no-op everywhere
+    assert lib.kbnet_upconv2x_forward(None, 0, 8, 4, 4, 128, None, 8, 1, 0.2, None, 512, None) == 0
+    assert lib.kbnet_outlier_removal_forward(None, None, 0, 8, 8, 7, 1.5, None, None, None, None) == 0
+    lib.kbnet_set_autotune(1)
+    lib.kbnet_set_autotune(0)
 
 
 def _ref_signature_strings():
