@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         // =================================================================================================================
         // converters: raw fp32 tile (shared) -> bf16 hi/lo chunk planes (shared), plus the generated chunks and z
         // =================================================================================================================
-        constexpr int MAXI = (GEO == G_S2K3 || GEO == G_S2K1) ? 2 : 4;
+        constexpr int MAXI = GEO == G_S2K3 ? 1 : (GEO == G_S2K1 ? 2 : 4);  // entries per converter thread (the four-plane path is the largest
+                                                                            // piece of code in the kernel: one item keeps it out of the I-cache's way)
         int it_e[MAXI], it_ei[MAXI], it_ej[MAXI], ro0[MAXI], ro1[MAXI];
         int n_it = 0;
 #pragma unroll
@@ -702,7 +703,7 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     if (geo == G_S2K3) { p.BW[1] = p.BW[0]; p.BH[1] = R + 1; }  // class 1 of the stride-2 programs: even rows only (sources read at even pixels)
     p.n_planes = geo == G_S2K3 ? 4 : 1;
     p.MB = cdiv(R * p.P, 128);
-    const int max_entries = (geo == G_S2K3 || geo == G_S2K1) ? 2 * V2_CONV_THREADS : 4 * V2_CONV_THREADS;
+    const int max_entries = (geo == G_S2K3 ? 1 : (geo == G_S2K1 ? 2 : 4)) * V2_CONV_THREADS;
     if (p.n_entries > max_entries || p.BW[0] > 256 || p.BH[0] > 256 || p.BW[1] > 256 || p.BH[1] > 256) return -1;
     p.plane_px = roundup(p.n_entries > max_shift + p.MB * 128 ? p.n_entries : max_shift + p.MB * 128, 8);
     int cols = 0, max_nsl = 0;
