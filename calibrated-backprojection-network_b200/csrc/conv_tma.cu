@@ -23,7 +23,7 @@
 // (free below N ~ 48, profiles/r01_umma_probe.md) and the epilogue adds the two column groups ("dual" mode).
 //
 // Roles (512 threads): warps 0-7 converters | warp 8 activation TMA | warp 9 weight TMA | warp 10 MMA issuer + TMEM
-// allocator | warps 12-15 epilogue (TMEM lane quarter = warp % 4).
+// allocator | warps 12-15 epilogue (TMEM lane quarter = warp % 4).  (warp counts: conv_warps(), cta_threads())
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,9 +46,11 @@ constexpr int V2_MAX_STAGES = 72;
 constexpr int V2_MAX_CONVS = 4;
 constexpr int V2_MAX_USES = 4;
 constexpr int V2_MAX_MAPS = 4;
-constexpr int V2_CONV_WARPS = 8;
-constexpr int V2_CONV_THREADS = V2_CONV_WARPS * 32;
-constexpr int V2_THREADS = 512;
+// converter warps per geometry (a multiple of 4: the epilogue warps sit at conv_warps + 4 .. + 7 and address TMEM lane quarter
+// warp % 4).  12 warps were measured for the stride-2 programs (they fit: ~80 registers) and changed nothing -- the KB block is
+// bound by the latency chain raw TMA -> convert -> MMA -> commit of its two operand stages, not by converter throughput.
+__host__ __device__ constexpr int conv_warps(int geo) { return geo >= 0 ? 8 : 8; }
+__host__ __device__ constexpr int cta_threads(int geo) { return (conv_warps(geo) + 8) * 32; }
 constexpr int V2_MAX_RAW = 6, V2_MAX_A = 3, V2_MAX_W = 8;
 constexpr int V2_HEADER = 2048;
 constexpr int V2_SMEM_LIMIT = 227 * 1024;
@@ -175,7 +177,7 @@ __device__ __forceinline__ TileCoord decode_tile(const V2Params& p, long long ti
 }
 
 template <int GEO, bool DUAL>
-__global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ V2Maps maps) {
+__global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ V2Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -186,16 +188,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
     uint8_t* sW = sA + (size_t)p.n_a * p.a_bytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CW = conv_warps(GEO), CONV_THREADS = CW * 32;  // roles: warps 0..CW-1 converters, CW raw TMA, CW+1 weights, CW+2 MMA, CW+4..CW+7 epilogue
 
     if (tid == 0) {
-        for (int i = 0; i < V2_MAX_RAW; ++i) { mbar_init(BAR(B_RAW_FULL + i), 1); mbar_init(BAR(B_RAW_EMPTY + i), V2_CONV_WARPS); }
-        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), V2_CONV_WARPS); mbar_init(BAR(B_A_EMPTY + i), 1); }
+        for (int i = 0; i < V2_MAX_RAW; ++i) { mbar_init(BAR(B_RAW_FULL + i), 1); mbar_init(BAR(B_RAW_EMPTY + i), CW); }
+        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), CW); mbar_init(BAR(B_A_EMPTY + i), 1); }
         for (int i = 0; i < V2_MAX_W; ++i) { mbar_init(BAR(B_W_FULL + i), 1); mbar_init(BAR(B_W_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACC_FULL + i), 1); mbar_init(BAR(B_ACC_EMPTY + i), 4); }
         fence_mbar_init();
     }
     if (tid < V2_MAX_ZC) s_wz[tid] = (p.w_proj != nullptr && tid < p.C_z) ? __ldg(p.w_proj + tid) : 0.f;
-    if (warp == 10) {
+    if (warp == CW + 2) {
         tmem_alloc_dyn(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const long long tile0 = blockIdx.x, tstep = gridDim.x;
 
-    if (warp < V2_CONV_WARPS) {
+    if (warp < CW) {
         // =================================================================================================================
         // converters: raw fp32 tile (shared) -> bf16 hi/lo chunk planes (shared), plus the generated chunks and z
         // =================================================================================================================
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
         int n_it = 0;
 #pragma unroll
         for (int i = 0; i < MAXI; ++i) {
-            const int e = tid + i * V2_CONV_THREADS;
+            const int e = tid + i * CONV_THREADS;
             it_e[i] = e;
             const int ei = e / p.P, ej = e - ei * p.P;
             it_ei[i] = ei; it_ej[i] = ej;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
                 a_r.advance((uint32_t)p.n_a);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == CW) {
         // =================================================================================================================
         // activation TMA producer (one thread)
         // =================================================================================================================
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == CW + 1) {
         // =================================================================================================================
         // weight producer (one thread): per (stage, use, tap) one slot = [chunk 0: hi rows, lo rows][chunk 1: hi rows, lo rows]
         // =================================================================================================================
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 10) {
+    } else if (warp == CW + 2) {
         // =================================================================================================================
         // MMA issuer.  The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
         // one elected lane issues (tcgen05.mma / commit are single-thread instructions).
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp >= 12) {
+    } else if (warp >= CW + 4) {
         // =================================================================================================================
         // epilogue: TMEM -> registers -> activation -> NCHW
         // =================================================================================================================
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_v2_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 10) tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == CW + 2) tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -703,7 +706,7 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     if (geo == G_S2K3) { p.BW[1] = p.BW[0]; p.BH[1] = R + 1; }  // class 1 of the stride-2 programs: even rows only (sources read at even pixels)
     p.n_planes = geo == G_S2K3 ? 4 : 1;
     p.MB = cdiv(R * p.P, 128);
-    const int max_entries = (geo == G_S2K3 ? 1 : (geo == G_S2K1 ? 2 : 4)) * V2_CONV_THREADS;
+    const int max_entries = (geo == G_S2K3 ? 1 : (geo == G_S2K1 ? 2 : 4)) * conv_warps(geo) * 32;
     if (p.n_entries > max_entries || p.BW[0] > 256 || p.BH[0] > 256 || p.BW[1] > 256 || p.BH[1] > 256) return -1;
     p.plane_px = roundup(p.n_entries > max_shift + p.MB * 128 ? p.n_entries : max_shift + p.MB * 128, 8);
     int cols = 0, max_nsl = 0;
@@ -791,8 +794,8 @@ std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks
                     const long long smem_min = apply_geometry(trial, R, TW, n_split, dual, has_up);
                     if (smem_min < 0 || smem_min > V2_SMEM_LIMIT) continue;
                     const double mma = mma_mb * trial.MB;
-                    const double items = (double)cdiv(trial.n_entries, V2_CONV_THREADS);
-                    const double cvt = (double)n_chunks * items * (trial.n_planes * 45.0 + 10.0) * V2_CONV_WARPS / 2.0 + p.n_stages * 150.0;
+                    const double items = (double)cdiv(trial.n_entries, conv_warps(geo) * 32);
+                    const double cvt = (double)n_chunks * items * (trial.n_planes * 45.0 + 10.0) * conv_warps(geo) / 2.0 + p.n_stages * 150.0;
                     double outb = 0;
                     for (int j = 0; j < p.n_convs; ++j) outb += (double)trial.conv[j].Nsl * R * TW * 4.0;
                     const double mem = ((double)n_tma_chunks * trial.raw_bytes + wbytes + outb) / 24.0;  // ~ one SM's share of HBM/L2, B/clk
@@ -861,10 +864,10 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     do {                                                                                                                      \
         if (p.dual) {                                                                                                         \
             KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));   \
-            conv_v2_kernel<G, true><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                           \
+            conv_v2_kernel<G, true><<<(unsigned)grid, cta_threads(G), (size_t)used, stream>>>(p, maps);                         \
         } else {                                                                                                              \
             KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));  \
-            conv_v2_kernel<G, false><<<(unsigned)grid, V2_THREADS, (size_t)used, stream>>>(p, maps);                          \
+            conv_v2_kernel<G, false><<<(unsigned)grid, cta_threads(G), (size_t)used, stream>>>(p, maps);                         \
         }                                                                                                                     \
     } while (0)
     if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
