@@ -728,7 +728,7 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     p.raw_bytes = roundup(raw0 > raw1 ? raw0 : raw1, 128);
     p.a_bytes = roundup(p.n_planes * 4 * p.plane_px * 16, 128);
     // weight-ring slot: as many taps of a 3x3 use as fit ~24 KB (one barrier round trip and one bulk copy per slot)
-    const int wcap = 24 * 1024;
+    static const int wcap = getenv("KBNET_V2_WCAP") ? atoi(getenv("KBNET_V2_WCAP")) : 24 * 1024;  // bytes of weights per ring slot (debugging aid)
     p.T = max_nsl * 64 * 9 <= wcap ? 9 : (max_nsl * 64 * 4 <= wcap ? 4 : (max_nsl * 64 * 3 <= wcap ? 3 : 1));
     int max_taps = 1;
     for (int j = 0; j < p.n_convs; ++j) max_taps = p.conv[j].ntaps > max_taps ? p.conv[j].ntaps : max_taps;
@@ -838,6 +838,13 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     grow(p.n_w, p.w_bytes, 4);
     grow(p.n_raw, p.raw_bytes, V2_MAX_RAW);
     grow(p.n_w, p.w_bytes, V2_MAX_W);
+    if (const char* ov = getenv("KBNET_V2_RINGS")) {  // debugging aid: "n_raw,n_a,n_w" (must fit shared memory)
+        int a, b, c;
+        if (sscanf(ov, "%d,%d,%d", &a, &b, &c) == 3 && a >= 2 && a <= V2_MAX_RAW && b >= 2 && b <= V2_MAX_A && c >= 2 && c <= V2_MAX_W) {
+            const long long u2 = (long long)V2_HEADER + (long long)a * p.raw_bytes + (long long)b * p.a_bytes + (long long)c * p.w_bytes;
+            if (u2 <= V2_SMEM_LIMIT) { p.n_raw = a; p.n_a = b; p.n_w = c; used = u2; }
+        }
+    }
     if (used < 120 * 1024) used = 120 * 1024;  // one CTA per SM (the TMEM budget assumes it)
 
     V2Maps maps;
