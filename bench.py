@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- KBNet forward frames/s @352x1216 on N x B200 (BASELINE.json metric), with the S2D / KB rooflines.
+"""bench.py -- KBNet forward frames/s on N x B200 (BASELINE.json metric), with the S2D / KB rooflines.
 
-  python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun for N>1)
-  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (oracle port), rank 0 only
+  python bench.py --gpus N --steps K --warmup W             # this framework (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's own PyTorch-CPU path, rank 0 only
+  python bench.py --impl torch-gpu --steps K ...             # the reference run eagerly on the B200 (stock cuDNN): GPU incumbent
+  python bench.py --workload void ...                        # BASELINE config 4 shapes (480x640, VOID pools), 8 frames per GPU
 
 A "step" = one forward of the full KBNet (S2D -> encoder with 4 KB layers -> decoder -> depth head) over a batch of
-8 synthetic KITTI-shaped frames per GPU (BASELINE config 3; config 5 is the same per-GPU work on 8 GPUs: weak scaling).
-Prints ONE JSON line on rank 0.
+8 synthetic frames per GPU (KITTI 352x1216: BASELINE config 3; config 5 is the same per-GPU work on 8 GPUs, weak scaling;
+VOID 480x640 at 8 frames per GPU on 4 GPUs is config 4).  Prints ONE JSON line on rank 0.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -22,29 +25,38 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = 'kbnet_fwd_frames_per_sec_352x1216'
-H, W = 352, 1216
-MIN_POOLS, MAX_POOLS = [5, 7, 9, 11, 13], [15, 17]
 F_IMG, F_DEP, F_DEC = [48, 96, 192, 384, 384], [16, 32, 64, 128, 128], [256, 128, 128, 64, 12]
-KITTI_K = [[721.5377, 0.0, 609.5593], [0.0, 721.5377, 172.854], [0.0, 0.0, 1.0]]
+WORKLOADS = {
+    # bash/kitti/run_kbnet_kitti_validation.sh:10-27
+    'kitti': dict(name='kbnet_kitti_352x1216_full_forward', metric='kbnet_fwd_frames_per_sec_352x1216', h=352, w=1216,
+                  min_pools=[5, 7, 9, 11, 13], max_pools=[15, 17], p=0.05, dmin=1.0, dmax=80.0, min_pred=1.5, max_pred=100.0,
+                  k=[[721.5377, 0.0, 609.5593], [0.0, 721.5377, 172.854], [0.0, 0.0, 1.0]]),
+    # bash/void/run_kbnet_void1500.sh:10-29
+    'void': dict(name='kbnet_void_480x640_full_forward', metric='kbnet_fwd_frames_per_sec_480x640', h=480, w=640,
+                 min_pools=[15, 17], max_pools=[23, 27, 29], p=0.005, dmin=0.2, dmax=7.0, min_pred=0.1, max_pred=8.0,
+                 k=[[514.6, 0.0, 319.5], [0.0, 514.6, 239.5], [0.0, 0.0, 1.0]]),
+}
 
 
-def synth_inputs(n, seed):
+def synth_inputs(cfg, n, seed):
     gen = torch.Generator().manual_seed(seed)
-    image = torch.rand(n, 3, H, W, generator=gen)
-    mask = (torch.rand(n, 1, H, W, generator=gen) < 0.05).float()
-    depth = (torch.rand(n, 1, H, W, generator=gen) * 79.0 + 1.0) * mask
+    h, w = cfg['h'], cfg['w']
+    image = torch.rand(n, 3, h, w, generator=gen)
+    mask = (torch.rand(n, 1, h, w, generator=gen) < cfg['p']).float()
+    depth = (torch.rand(n, 1, h, w, generator=gen) * (cfg['dmax'] - cfg['dmin']) + cfg['dmin']) * mask
     valid = (depth > 0).float()
-    k = torch.tensor(KITTI_K, dtype=torch.float32).view(1, 3, 3).repeat(n, 1, 1)
+    k = torch.tensor(cfg['k'], dtype=torch.float32).view(1, 3, 3).repeat(n, 1, 1)
     return image, depth, valid, k
 
 
 def ncu_traffic(key):
-    """dram bytes of one launch of the kernel, from the committed ncu capture (profiles/r01_traffic.json); None if absent"""
-    try:
-        return float(json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))[key]['traffic'])
-    except Exception:
-        return None
+    """dram bytes of one launch of the kernel, from the committed ncu capture (profiles/traffic.json); None if absent"""
+    for name in ('traffic.json', 'r01_traffic.json'):
+        try:
+            return float(json.load(open(os.path.join(ROOT, 'profiles', name)))[key]['traffic'])
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -53,6 +65,32 @@ def peaks():
         return float(p['hbm_gbs']), float(p['bf16_tflops']), float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), 'measured'
     except Exception:
         return 6650.0, 1590.0, 1400.0, 'fallback'
+
+
+def pin_to_gpu_numa_node(index):
+    """Bind this process to the CPUs NVML reports as local to the GPU (H2D copies from pinned memory then stay on the
+    socket the GPU hangs off).  Best effort: returns a short description, never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return '%d cpus local to gpu %d' % (len(cpus), phys)
+        return 'nvml reported no local cpus'
+    except Exception as e:  # noqa: BLE001
+        return 'not pinned (%s)' % type(e).__name__
 
 
 class ClockSampler(threading.Thread):
@@ -124,64 +162,146 @@ class ClockSampler(threading.Thread):
                 'power_w_max': pw, 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
-def cpu_forward_fn():
-    """The reference's CPU path for this workload: the oracle's op-for-op restatement (same ATen CPU ops as the
-    reference modules; /root/reference itself does not exist on the GPU box)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own implementation of the path (baseline/_ref = the unmodified reference; else the oracle port)
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_forward_fn(cfg, device):
+    """-> (forward(image, depth, valid, k) -> depth, kind, description).  kind 'reference' = the unmodified reference
+    (kbnet_model.KBNetModel from baseline/_ref or /root/reference, eval, no_grad); 'port' = oracle/kbnet_oracle.py, the
+    op-for-op restatement of the same ATen sequence (used only when no copy of the reference travelled)."""
+    from oracle import refload
+    model = None
+    try:
+        model = refload.build_reference_model(cfg, device, F_IMG, F_DEP, F_DEC, seed=0)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write('bench: reference import failed (%s); using the oracle port\n' % e)
+    if model is not None:
+        model.eval()
+
+        def fwd(image, depth, valid, k):
+            with torch.no_grad():
+                return model.forward(image, depth, valid, k)
+        return fwd, 'reference', 'unmodified reference kbnet_model.KBNetModel.forward (%s)' % refload.reference_dir()
     from oracle import kbnet_oracle as K
-    ws, we, wd = K.make_model_weights(torch.Generator().manual_seed(0), 2, 7, 8, 3, F_IMG, F_DEP, F_DEC)
+    n_pool = len(cfg['min_pools']) + len(cfg['max_pools'])
+    ws, we, wd = K.make_model_weights(torch.Generator().manual_seed(0), 2, n_pool, 8, 3, F_IMG, F_DEP, F_DEC)
+    ws, we, wd = ({k_: v.to(device) for k_, v in d.items()} for d in (ws, we, wd))
 
     def fwd(image, depth, valid, k):
         with torch.no_grad():
-            return K.model_forward(image, depth, valid, k, ws, we, wd, MIN_POOLS, MAX_POOLS, 1.5, 100.0)
-    return fwd
+            return K.model_forward(image, depth, valid, k, ws, we, wd, cfg['min_pools'], cfg['max_pools'], cfg['min_pred'], cfg['max_pred'])
+    return fwd, 'port', 'oracle port of the reference PyTorch path (same ATen ops)'
 
 
-def run_reference(args, rank):
-    """--impl reference: CPU reference path, all host threads, rank 0 only."""
+def run_reference(args, rank, cfg):
+    """--impl reference: the reference's CPU path, all host threads, rank 0 only, same config as the GPU arm."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    fwd = cpu_forward_fn()
-    nb = args.cpu_batch
-    inp = synth_inputs(nb, 1)
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):   # one warm-up pass is enough on the CPU
-        fwd(*inp)
+    fwd, kind, desc = reference_forward_fn(cfg, torch.device('cpu'))
+    nb = args.cpu_batch or args.batch
+    inp = synth_inputs(cfg, nb, 1)
+    t0 = time.perf_counter()
+    fwd(*inp)                                   # one warm-up pass is enough on the CPU
+    t_est = time.perf_counter() - t0
+    # bounded: the whole run has to end within a few minutes whatever K the caller asks for
+    steps = max(2, min(args.steps, int(args.cpu_budget_s / max(t_est, 1e-3))))
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
         fwd(*inp)
         times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
     val = nb / t
-    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'kbnet_kitti_352x1216_full_forward', 'frames_per_step': nb, 'device': 'cpu'},
-            'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d frames per step, oracle port of the reference PyTorch-CPU path (same ATen ops)' % nb},
+    line = {'impl': 'reference', 'metric': cfg['metric'], 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
+            'steps_requested': args.steps, 'warmup': 1, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': cfg['name'], 'frames_per_gpu_per_step': nb, 'frames_per_step': nb, 'device': 'cpu',
+                       'pools': {'min': cfg['min_pools'], 'max': cfg['max_pools']}},
+            'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                             'sample': '%d steps of %d frames (the GPU arm\'s batch), %s' % (steps, nb, desc)},
             'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+def time_gpu_incumbent(cfg, dev, nb, steps, warmup, tf32):
+    """The reference run eagerly on the B200 through stock PyTorch / cuDNN (the GPU incumbent): CUDA events
+    around `steps` forwards with inputs resident on the device.  -> (frames/s, ms per step, kind)"""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+    try:
+        fwd, kind, _ = reference_forward_fn(cfg, dev)
+        inp = [t.to(dev) for t in synth_inputs(cfg, nb, 1)]
+        for _ in range(warmup):
+            fwd(*inp)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fwd(*inp)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        del out
+        return nb / (ms * 1e-3), ms, kind
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def run_torch_gpu(args, rank, cfg):
+    """--impl torch-gpu: the GPU incumbent as its own line (rank 0 only)."""
+    if rank != 0:
+        return
+    assert torch.cuda.is_available()
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    res = {}
+    for tf32 in (True, False):
+        fps, ms, kind = time_gpu_incumbent(cfg, dev, args.batch, args.steps, max(args.warmup, 3), tf32)
+        res['tf32_on' if tf32 else 'tf32_off'] = {'value': fps, 'ms_per_step': ms}
+    line = {'impl': 'torch-gpu', 'metric': cfg['metric'], 'value': res['tf32_on']['value'], 'unit': 'frames/s', 'n_gpus': 1,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': res['tf32_on']['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (cuDNN, allow_tf32 on; off in gpu_incumbent.tf32_off)', 'data': 'synthetic',
+            'config': {'workload': cfg['name'], 'frames_per_gpu_per_step': args.batch, 'device': 'cuda', 'kind': kind},
+            'gpu_incumbent': res}
+    print(json.dumps(line))
+
+
+def sha256_of(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='kbnet', choices=['kbnet', 'reference'])
+    ap.add_argument('--impl', default='kbnet', choices=['kbnet', 'reference', 'torch-gpu'])
+    ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=8, help='frames per GPU per step')
-    ap.add_argument('--cpu-batch', type=int, default=2, help='frames per step of the CPU reference sample')
+    ap.add_argument('--cpu-batch', type=int, default=0, help='frames per step of the CPU reference (0 = the GPU arm\'s batch)')
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='upper bound on the CPU reference arm\'s timed region')
     ap.add_argument('--conv-backend', default=None, choices=['kbnet', 'torch'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-incumbent', action='store_true')
     ap.add_argument('--no-autotune', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel of the forward individually (no CUDA graph)')
+    ap.add_argument('--no-shard-check', action='store_true')
     args = ap.parse_args()
 
+    cfg = WORKLOADS[args.workload]
+    H, W = cfg['h'], cfg['w']
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
-        run_reference(args, rank)
+        run_reference(args, rank, cfg)
+        return
+    if args.impl == 'torch-gpu':
+        run_torch_gpu(args, rank, cfg)
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -193,6 +313,7 @@ def main():
         M.CONV_BACKEND = args.conv_backend
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    affinity = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -201,17 +322,18 @@ def main():
     kbnet_b200.set_autotune(not args.no_autotune)     # tile plans are measured during the warm-up steps
 
     torch.manual_seed(0 if rank == 0 else 1234 + rank)         # only rank 0's weights survive the broadcast
-    model = kbnet_b200.KBNetModel(3, 2, MIN_POOLS, MAX_POOLS, 3, 8, F_IMG, F_DEP, [0, 1, 2, 3], F_DEC, deconv_type='up',
+    model = kbnet_b200.KBNetModel(3, 2, cfg['min_pools'], cfg['max_pools'], 3, 8, F_IMG, F_DEP, [0, 1, 2, 3], F_DEC, deconv_type='up',
                                   weight_initializer='xavier_normal', activation_func='leaky_relu',
-                                  min_predict_depth=1.5, max_predict_depth=100.0, device=dev)
+                                  min_predict_depth=cfg['min_pred'], max_predict_depth=cfg['max_pred'], device=dev)
     bcast_bytes = kbnet_b200.dist.broadcast_parameters(model.parameters(), src=0) if world > 1 else 0
 
     nb = args.batch
-    host = [t.pin_memory() for t in synth_inputs(nb, 1 + rank)]
+    # shard r of the global batch = synth_inputs(seed 1 + r): rank r runs shard r
+    host = [t.pin_memory() for t in synth_inputs(cfg, nb, 1 + rank)]
     resident = [t.to(dev) for t in host]
-    out_host = torch.empty((nb, 1, H, W), dtype=torch.float32).pin_memory()
+    out_host = [torch.empty((nb, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
     h2d = sum(t.numel() * 4 for t in host)
-    d2h = out_host.numel() * 4
+    d2h = out_host[0].numel() * 4
 
     # per-kernel CUDA events on the launching stream (torch's current stream) around the S2D call
     s2d_events = []
@@ -225,9 +347,8 @@ def main():
         e1.record()
         s2d_events.append((e0, e1))
         return y
-    s2d_mod.forward = timed_s2d
 
-    # ... and around KB block 2 (BASELINE config 2 is exactly this call at 8 frames: 48/16/48 ch @176x608 -> 96/32/96 @88x304)
+    # ... and around KB block 2 (BASELINE config 2 is exactly this call at 8 KITTI frames: 48/16/48 ch @176x608 -> 96/32/96 @88x304)
     kb_events = []
     kb2 = model.encoder.calibrated_backprojection2
     kb2_forward = kb2.forward
@@ -239,18 +360,37 @@ def main():
         e1.record()
         kb_events.append((e0, e1))
         return y
-    kb2.forward = timed_kb2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- warm-up (tile autotuning happens here), then the per-kernel roofline pass with events inside the step -----------
     for _ in range(args.warmup):
         model.forward(*resident)
     barrier()
-    s2d_events.clear()
-    kb_events.clear()
+    s2d_mod.forward, kb2.forward = timed_s2d, timed_kb2
+    n_roof = max(10, min(args.steps, 50))
+    for _ in range(n_roof):
+        model.forward(*resident)
+    barrier()
+    s2d_mod.forward, kb2.forward = orig_forward, kb2_forward
+    s2d_ms = sum(a.elapsed_time(b) for a, b in s2d_events) / max(len(s2d_events), 1)
+    kb_ms = sum(a.elapsed_time(b) for a, b in kb_events) / max(len(kb_events), 1)
+
+    # ---- the step: eager launches, or one CUDA graph of the whole forward (static input / output buffers) ------------------
+    use_graph = not args.no_graph and hasattr(model, 'capture')
+    runner = model.capture(*resident) if use_graph else None
+
+    def step_resident():
+        if runner is not None:
+            return runner.replay()
+        return model.forward(*resident)
+
+    for _ in range(3):
+        step_resident()
+    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -258,32 +398,42 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        out = model.forward(*resident)
+        out = step_resident()
     e1.record()
     barrier()
-    launches = lib.kbnet_launch_count() - n0
+    launches_counted = lib.kbnet_launch_count() - n0
     ms = e0.elapsed_time(e1)
-    s2d_ms = sum(a.elapsed_time(b) for a, b in s2d_events) / max(len(s2d_events), 1)
-    kb_ms = sum(a.elapsed_time(b) for a, b in kb_events) / max(len(kb_events), 1)
+    shard_sha = sha256_of(out)
+    launches_per_step = runner.launches_per_step if runner is not None else launches_counted // max(args.steps, 1)
+    launches = launches_per_step * args.steps
     tma_launches = lib.kbnet_tma_engine_launch_count()
 
-    # end-to-end through the public API: every step copies ITS inputs from pinned host memory and reads ITS result back.
-    # Two device input sets + a copy stream: the H2D of step i+1 overlaps the forward of step i (the usual serving pipeline).
-    copy_stream = torch.cuda.Stream(device=dev)
+    # ---- end to end through the public API: every step copies ITS inputs from pinned host memory and reads ITS result back.
+    # Two device input sets + a copy stream for H2D and another for D2H: the H2D of step i+1 and the D2H of step i-1 overlap
+    # the forward of step i (the usual serving pipeline).
+    h2d_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    if runner is not None:
+        dev_in = [runner.static_inputs, [torch.empty_like(t, device=dev) for t in host]]
+        runners = [runner, model.capture(*dev_in[1])]
+    else:
+        dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+        runners = [None, None]
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
+    out_ready = [torch.cuda.Event() for _ in range(2)]
+    out_free = [torch.cuda.Event() for _ in range(2)]
 
     def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(in_free[slot])
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(in_free[slot])
             for d, h in zip(dev_in[slot], host):
                 d.copy_(h, non_blocking=True)
-            in_ready[slot].record(copy_stream)
+            in_ready[slot].record(h2d_stream)
 
     def e2e_loop(n_steps):
-        for ev in in_free:
+        for ev in in_free + out_free:
             ev.record(main_stream)
         upload(0)
         for i in range(n_steps):
@@ -291,19 +441,39 @@ def main():
             if i + 1 < n_steps:
                 upload(slot ^ 1)
             main_stream.wait_event(in_ready[slot])
-            out_host.copy_(model.forward(*dev_in[slot]), non_blocking=True)
+            main_stream.wait_event(out_free[slot])          # the D2H that last read this slot's output buffer has finished
+            y = runners[slot].replay() if runners[slot] is not None else model.forward(*dev_in[slot])
             in_free[slot].record(main_stream)
+            out_ready[slot].record(main_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(out_ready[slot])
+                out_host[slot].copy_(y, non_blocking=True)
+                out_free[slot].record(d2h_stream)
+                y.record_stream(d2h_stream)
+        main_stream.wait_stream(d2h_stream)
+        main_stream.wait_stream(h2d_stream)
 
-    e2e_loop(2)
+    e2e_loop(4)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     e2e_loop(args.steps)
-    copy_stream.synchronize()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    e2e_sha = hashlib.sha256(out_host[(args.steps - 1) & 1].numpy().tobytes()).hexdigest()[:16]
     clocks = sampler.summary() if rank == 0 else None
+
+    # ---- N ranks == 1 rank, on hardware: SHA-256 of every shard's output.  Rank r reports shard r; a single-GPU run also
+    # computes shards 1..7 (outside the timed regions) so that its list can be compared with an 8-GPU run's list.
+    shard_shas = [shard_sha]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, shard_sha)
+        shard_shas = gathered
+    elif not args.no_shard_check:
+        for r in range(1, 8):
+            shard_shas.append(sha256_of(model.forward(*[t.to(dev) for t in synth_inputs(cfg, nb, 1 + r)])))
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, s2d_ms, kb_ms], device=dev, dtype=torch.float64)
@@ -321,47 +491,72 @@ def main():
     s2d_bytes = 4.0 * H * W * (2 + 8) * nb                    # 4*H*W*(C_in + n_filter) per frame
     s2d_gbs = s2d_bytes / (s2d_ms * 1e-3) / 1e9 if s2d_ms > 0 else 0.0
     # KB block 2 (fast path): image 48ch + depth 16ch full reads, fused 48ch at even pixels, three outputs
-    kb_bytes = 4.0 * nb * ((48 + 16) * 176 * 608 + 48 * 88 * 304 + (96 + 32 + 96) * 88 * 304)
-    kb_flops = 24.19e9 * nb / 8.0
+    h1, w1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    h2, w2 = (h1 - 1) // 2 + 1, (w1 - 1) // 2 + 1
+    kb_bytes = 4.0 * nb * ((48 + 16) * h1 * w1 + 48 * h2 * w2 + (96 + 32 + 96) * h2 * w2)
+    kb_flops = 2.0 * nb * h2 * w2 * (96 * 48 * 9 + 32 * 19 * 9 + 96 * 99) + 2.0 * nb * h1 * w1 * 16
     kb_gbs = kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0
+    is_kitti8 = args.workload == 'kitti' and nb == 8
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': cfg['metric'], 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'kbnet_kitti_352x1216_full_forward', 'frames_per_gpu_per_step': nb, 'global_batch': nb * world,
-                   'pools': {'min': MIN_POOLS, 'max': MAX_POOLS}, 'parallelism': 'batch-sharded x%d, weights broadcast once (%d B)' % (world, bcast_bytes),
+        'config': {'workload': cfg['name'], 'frames_per_gpu_per_step': nb, 'global_batch': nb * world,
+                   'pools': {'min': cfg['min_pools'], 'max': cfg['max_pools']}, 'parallelism': 'batch-sharded x%d, weights broadcast once (%d B)' % (world, bcast_bytes),
                    'conv_backend_outside_hot_path': M.CONV_BACKEND, 'tile_autotune': not args.no_autotune,
+                   'cuda_graph': runner is not None, 'cpu_affinity': affinity,
                    'l2': 'per-step activations (>2 GB at batch 8) far exceed the 126 MB L2; no explicit flush',
-                   'e2e_pipeline': 'double-buffered pinned H2D on a copy stream overlapped with the previous forward; D2H of every result'},
+                   'e2e_pipeline': 'double-buffered pinned H2D on a copy stream and D2H of every result on a second copy stream, both overlapped with the forward',
+                   'roofline_pass': '%d eager steps with CUDA events around the S2D and KB-block-2 launches (inside the step, before the timed region)' % n_roof},
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps, 'output_sha256_16': e2e_sha, 'output_equals_resident_run': e2e_sha == shard_sha},
         'gpu_launches': int(launches),
+        'gpu_launches_per_step': int(launches_per_step),
         'clocks': clocks,
-        'roofline': {'kernel': 's2d_fused_kernel', 'bound': 'hbm', 'achieved': s2d_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': s2d_gbs / hbm_peak, 'traffic': ncu_traffic('s2d_fused_kernel') if nb == 8 else None, 'peak_kind': peak_kind,
+        'shard_output_sha256_16': shard_shas,
+        'roofline': {'kernel': 's2d kernel (SparseToDensePool, one launch)', 'bound': 'hbm', 'achieved': s2d_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': s2d_gbs / hbm_peak, 'traffic': ncu_traffic('s2d_fused_kernel') if is_kitti8 else None, 'peak_kind': peak_kind,
                      'algorithmic_bytes_per_launch': s2d_bytes, 'ms_per_launch': s2d_ms,
-                     'traffic_note': 'dram__bytes_read+write of one launch, ncu --set full, profiles/r01_traffic.json'},
-        'roofline_kb': {'kernel': 'conv_v2_kernel<S2K3> (fused KB block 2 = BASELINE config 2)', 'bound': 'hbm', 'achieved': kb_gbs,
-                        'peak': hbm_peak, 'unit': 'GB/s', 'frac': kb_gbs / hbm_peak, 'traffic': ncu_traffic('kb_block2_fused') if nb == 8 else None,
+                     'traffic_note': 'dram__bytes_read+write of one launch, ncu --set full, profiles/traffic.json'},
+        'roofline_kb': {'kernel': 'fused KB block 2 (BASELINE config 2 at the KITTI workload)', 'bound': 'hbm', 'achieved': kb_gbs,
+                        'peak': hbm_peak, 'unit': 'GB/s', 'frac': kb_gbs / hbm_peak, 'traffic': ncu_traffic('kb_block2_fused') if is_kitti8 else None,
                         'peak_kind': peak_kind,
                         'algorithmic_bytes_per_launch': kb_bytes, 'ms_per_launch': kb_ms,
                         'tensor_tflops_bf16_issued': 3.0 * kb_flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0,
                         'tensor_peak_tflops': tf_sus},
         'tma_engine_launches_total': int(tma_launches),
     }
+    if world == 1 and not args.no_gpu_incumbent:
+        # the GPU incumbent: the reference eagerly on this B200 through stock cuDNN, same inputs and batch
+        try:
+            inc = {}
+            for tf32 in (True, False):
+                fps, ms_i, kind = time_gpu_incumbent(cfg, dev, nb, 10, 3, tf32)
+                inc['tf32_on' if tf32 else 'tf32_off'] = {'value': fps, 'ms_per_step': ms_i}
+            inc['kind'] = kind
+            inc['unit'] = 'frames/s'
+            inc['note'] = 'reference forward, eager PyTorch %s + cuDNN on the same GPU, inputs resident, CUDA events, 10 steps' % torch.__version__
+            line['gpu_incumbent'] = inc
+        except Exception as e:  # noqa: BLE001
+            line['gpu_incumbent'] = {'unavailable': '%s: %s' % (type(e).__name__, e)}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        try:
+            os.sched_setaffinity(0, range(cores))           # undo the GPU-local pinning: the CPU arm uses every host core
+        except Exception:  # noqa: BLE001
+            pass
         torch.set_num_threads(cores)
-        fwd = cpu_forward_fn()
-        cb = args.cpu_batch
-        inp = synth_inputs(cb, 1)
+        fwd, kind, desc = reference_forward_fn(cfg, torch.device('cpu'))
+        cb = args.cpu_batch or nb
+        inp = synth_inputs(cfg, cb, 1)
         fwd(*[t[:1] for t in inp])
+        n_pass = 3
         t0 = time.perf_counter()
-        fwd(*inp)
-        dt = time.perf_counter() - t0
-        line['cpu_baseline'] = {'value': cb / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                'sample': '%d frames, one pass after a 1-frame warm-up, oracle port of the reference '
-                                          'PyTorch-CPU path' % cb}
+        for _ in range(n_pass):
+            fwd(*inp)
+        dt = (time.perf_counter() - t0) / n_pass
+        line['cpu_baseline'] = {'value': cb / dt, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                                'sample': '%d passes of %d frames (the GPU arm\'s batch) after a 1-frame warm-up, %s' % (n_pass, cb, desc)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -6,7 +6,7 @@ contract asks for).  The compute lives in libkbnet_b200.so (csrc/, C ABI in incl
 """
 from . import _lib, build as _build, dist, ops
 from .modules import CalibratedBackprojectionBlock, OutlierRemoval, SparseToDensePool, install, set_precision, get_precision
-from .model import KBNetEncoder, KBNetModel, MultiScaleDecoder
+from .model import GraphRunner, KBNetEncoder, KBNetModel, MultiScaleDecoder
 
 __all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'OutlierRemoval', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
            'install', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']

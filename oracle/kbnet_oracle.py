@@ -79,17 +79,17 @@ def s2d_forward(x, weights, min_pool_sizes, max_pool_sizes, slope=LEAKY_SLOPE, r
 # --------------------------------------------------------------------------------------
 # Camera coordinates / intrinsics scaling
 # --------------------------------------------------------------------------------------
-def meshgrid_h(n, h, w):
+def meshgrid_h(n, h, w, device=None):
     """src/net_utils.py:1601-1636: [N,3,H,W] homogeneous pixel grid (x = col, y = row, 1)."""
-    xs = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(n, 1, h, w)
-    ys = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1).expand(n, 1, h, w)
-    return torch.cat([xs, ys, torch.ones(n, 1, h, w)], dim=1)
+    xs = torch.arange(w, dtype=torch.float32, device=device).view(1, 1, 1, w).expand(n, 1, h, w)
+    ys = torch.arange(h, dtype=torch.float32, device=device).view(1, 1, h, 1).expand(n, 1, h, w)
+    return torch.cat([xs, ys, torch.ones(n, 1, h, w, device=device)], dim=1)
 
 
 def camera_coordinates(k, h, w):
     """src/networks.py:317-331: coordinates = inverse(K) @ [x, y, 1]  ->  [N,3,H,W]."""
     n = k.shape[0]
-    xy_h = meshgrid_h(n, h, w).reshape(n, 3, -1)
+    xy_h = meshgrid_h(n, h, w, k.device).reshape(n, 3, -1)
     return torch.matmul(torch.inverse(k), xy_h).view(n, 3, h, w)
 
 
@@ -99,7 +99,7 @@ def scale_intrinsics_level1(k, h0, w0, h1, w1):
     K * [[sx,1,sx],[1,sy,sy],[1,1,1]] with sx = W1/W0, sy = H1/H0."""
     sx = w1 / w0
     sy = h1 / h0
-    scale = torch.tensor([[sx, 1.0, sx], [1.0, sy, sy], [1.0, 1.0, 1.0]], dtype=torch.float32)
+    scale = torch.tensor([[sx, 1.0, sx], [1.0, sy, sy], [1.0, 1.0, 1.0]], dtype=torch.float32, device=k.device)
     return k * scale.view(1, 3, 3)
 
 
