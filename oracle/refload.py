@@ -45,10 +45,17 @@ def build_reference_model(cfg, device, f_img, f_dep, f_dec, seed=0):
         return None
     kbnet_model = mods[2]
     torch.manual_seed(seed)
-    return kbnet_model.KBNetModel(
+    model = kbnet_model.KBNetModel(
         input_channels_image=3, input_channels_depth=2,
         min_pool_sizes_sparse_to_dense_pool=cfg['min_pools'], max_pool_sizes_sparse_to_dense_pool=cfg['max_pools'],
         n_convolution_sparse_to_dense_pool=3, n_filter_sparse_to_dense_pool=8,
         n_filters_encoder_image=list(f_img), n_filters_encoder_depth=list(f_dep), resolutions_backprojection=[0, 1, 2, 3],
         n_filters_decoder=list(f_dec), deconv_type='up', weight_initializer='xavier_normal', activation_func='leaky_relu',
         min_predict_depth=cfg['min_pred'], max_predict_depth=cfg['max_pred'], device=device)
+    if torch.device(device).type == 'cpu':
+        # src/kbnet_model.py:408-415 wraps every network in torch.nn.DataParallel; on a box WITH GPUs the wrapper insists on
+        # cuda:0 parameters.  An empty device_ids list is DataParallel's own CPU pass-through (what it does on a GPU-less
+        # box) -- a setting on the torch wrapper object, the reference code is untouched.
+        for net in (model.sparse_to_dense_pool, model.encoder, model.decoder):
+            net.device_ids = []
+    return model
