@@ -45,19 +45,20 @@ using namespace ptx;
 typedef unsigned long long u64;
 
 constexpr int NF = 8;            // n_filter of the fast path
-constexpr int TH = 12, TW = 64;  // output tile
-constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+12  (14 x 17 = 238 strips: one round of 256 threads)
-constexpr int LV = 5;            // pass-1 rows per work item
-constexpr int PHV = 15;          // rows of the V planes = 3 * LV (one more than PH)
+constexpr int TH = 16, TW = 64;  // output tile (352 = 22 x 16, 480 = 30 x 16, 1216 = 19 x 64, 640 = 10 x 64: no partial tiles)
+constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+16  (18 x 17 = 306 strips: one round of 320 threads)
+constexpr int LV = 9;            // pass-1 rows per work item (two items per tile column)
 constexpr int PW = TW + 4;       // conv-input cols   x0-2 .. x0+65  (17 strips of 4)
 constexpr int XP = PW + 4;       // smem pitch of the raw-channel tile: TMA boxes start at x0-4 (16-byte aligned coordinate)
-constexpr int NT = 256;
+constexpr int XCP = PW + 1;      // pitch of the packed raw-channel planes: entry PW of every row is zero (unused mma k-slots read it)
+constexpr int NT = 320;
+constexpr int CONV_WARPS = 8;    // phase D: 4 column blocks x 2 row groups
 constexpr int LH = 4;            // pass-2 strip width
 constexpr int MAX_POOL = 16;
 constexpr int MAX_CONV = 8;
-constexpr int SMEM_2CTA = 113 * 1024;
+constexpr int SMEM_MAX = 200 * 1024;   // beyond this the generic kernel takes the configuration (shipped ones need ~100 KB: 2 CTAs / SM)
 constexpr int WB_BYTES = 6 * 2 * 32 * 8;
-static_assert(PHV % LV == 0 && PHV >= PH && PW % LH == 0 && TH % 2 == 0, "tiling");
+static_assert(PH % LV == 0 && PW % LH == 0 && TH % 2 == 0, "tiling");
 
 struct PoolSpec {            // canonical plane order: min pools by ascending radius, then max pools by ascending radius
     int n_pool, n_min;
@@ -88,20 +89,21 @@ struct FastParams {
     int use_tma;
 };
 
-__host__ __device__ inline int w1d_bytes(int n_pool, int n_conv) { return (((NF * n_pool + (n_conv - 1) * NF * NF) * 8) + 15) & ~15; }
+__host__ __device__ inline int w1_bytes(int n_pool, int n_conv) { return (((NF * n_pool + (n_conv - 1) * NF * NF) * 4) + 15) & ~15; }
 
 struct Layout {  // byte offsets into dynamic shared memory (same function on host and device)
-    int w1d, wB, xc, v, z, x1, qhi, qlo, total;
+    int w1, wB, xch, xcl, v, z, x1, qhi, qlo, total;
 };
 __host__ __device__ inline Layout make_layout(int R, int n_pool, int n_conv) {
-    const int ZW = PW + 2 * R, ZH = PHV + 2 * R, ZP = ZW + 4;
+    const int ZW = PW + 2 * R, ZH = PH + 2 * R, ZP = ZW + 4;
     Layout L;
     int o = 16;  // [0,8): mbarrier
-    L.w1d = o; o += w1d_bytes(n_pool, n_conv);
+    L.w1 = o; o += w1_bytes(n_pool, n_conv);
     L.wB = o; o += WB_BYTES;
-    L.xc = o; o += PH * PW * 8;
+    L.xch = o; o += PH * XCP * 8;
+    L.xcl = o; o += PH * XCP * 8;
     o = (o + 15) & ~15;
-    L.v = o; o += n_pool * PHV * ZW * 4;
+    L.v = o; o += n_pool * PH * ZW * 4;
     o = (o + 127) & ~127;
     L.z = o;                                       // union: {z tile, x1 tile} (dead after phase B)  /  {Q hi, Q lo}
     L.x1 = (L.z + ZH * ZP * 4 + 127) & ~127;
@@ -124,6 +126,7 @@ __host__ __device__ constexpr int nth_bit(unsigned m, int k) {  // position of t
         }
     return 0;
 }
+__host__ __device__ constexpr int top_bit(unsigned m) { int p = 0; for (int i = 0; i < 32; ++i) if ((m >> i) & 1u) p = i; return p; }
 
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
     u64 r;
@@ -141,12 +144,15 @@ __device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// w * (x0, x1) + (c0, c1): ptxas turns the (w, w) pair into the scalar-broadcast operand form of FFMA2 (no register copy)
+__device__ __forceinline__ u64 ffma2s(float w, u64 x, u64 c) { return ffma2(pack2(w, w), x, c); }
+__device__ __forceinline__ u64 fmul2s(float w, u64 x) { return fmul2(pack2(w, w), x); }
 // LeakyReLU for 0 <= slope <= 1:  max(v, slope * v)  (NaN stays NaN: both operands are NaN)
 __device__ __forceinline__ float leaky01(float v, float slope) { return fmaxf(v, v * slope); }
-__device__ __forceinline__ u64 leaky01x2(u64 v, u64 slope2) {
+__device__ __forceinline__ u64 leaky01x2(u64 v, float slope) {
     float a, b, sa, sb;
     unpack2(v, a, b);
-    unpack2(fmul2(v, slope2), sa, sb);
+    unpack2(fmul2s(slope, v), sa, sb);
     return pack2(fmaxf(a, sa), fmaxf(b, sb));
 }
 // two fp32 -> packed bf16 (a in the low half), round to nearest
@@ -185,25 +191,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
                  : "memory");
 }
 
-// ---- weight image: [w1d : 1x1 weights duplicated (w, w), layer 0 as [canonical plane][j], layers >= 1 as [k][j]]
-//                    [wB  : 3x3 weights as per-lane mma B fragments [kstep = dy*2 + half][hi|lo][lane] -> (b0, b1)]
+// ---- weight image: [w1 : 1x1 weights as plain floats, layer 0 as [canonical plane][j], layers >= 1 as [k][j]]
+//                    [wB : 3x3 weights as per-lane mma B fragments [kstep = dy*2 + half][hi|lo][lane] -> (b0, b1)]
 //   half 0: k 0-7 = Q channels at dx 0, k 8-15 = Q channels at dx 1;  half 1: k 0-7 = Q at dx 2, k 8-15 = raw x slots
 //   (slot s = c + C_in * dx, s < 3 * C_in).  B fragment: n = lane / 4, b0 holds k = 2t, 2t+1, b1 holds k = 2t+8, 2t+9.
 __device__ __forceinline__ void build_weight_image(const WeightSrc& ws, uint8_t* dst, int tid, int nthreads) {
-    float2* w1d = reinterpret_cast<float2*>(dst);
+    float* w1 = reinterpret_cast<float*>(dst);
     const int np = ws.n_pool;
     for (int i = tid; i < NF * np; i += nthreads) {
         const int k = i / NF, j = i - k * NF;
-        const float w = __ldg(ws.w1x1[0] + j * np + ws.chan[k]);
-        w1d[i] = make_float2(w, w);
+        w1[i] = __ldg(ws.w1x1[0] + j * np + ws.chan[k]);
     }
     for (int l = 1; l < ws.n_conv; ++l)
         for (int i = tid; i < NF * NF; i += nthreads) {
             const int k = i >> 3, j = i & 7;
-            const float w = __ldg(ws.w1x1[l] + j * NF + k);
-            w1d[NF * np + (l - 1) * NF * NF + i] = make_float2(w, w);
+            w1[NF * np + (l - 1) * NF * NF + i] = __ldg(ws.w1x1[l] + j * NF + k);
         }
-    uint32_t* wB = reinterpret_cast<uint32_t*>(dst + w1d_bytes(np, ws.n_conv));
+    uint32_t* wB = reinterpret_cast<uint32_t*>(dst + w1_bytes(np, ws.n_conv));
     const int ctot = NF + ws.C_in;
     for (int i = tid; i < 6 * 32 * 2; i += nthreads) {
         const int reg = i & 1, lane = (i >> 1) & 31, ks = i >> 6;
@@ -232,65 +236,70 @@ __device__ __forceinline__ void build_weight_image(const WeightSrc& ws, uint8_t*
 
 __global__ void s2d_pack_weights_kernel(const WeightSrc ws, uint8_t* dst) { build_weight_image(ws, dst, threadIdx.x, blockDim.x); }
 
-// ---- pass 1: vertical nested-window sweep of one tile column segment -----------------------------------------------
+// ---- pass 1: vertical nested-window sweep of one tile column, LV = 7 rows per thread -----------------------------------
 // MINM / MAXM >= 0: the pool configuration is a compile-time constant (bit r set <=> a pool of radius r), so every mask test,
 // plane index and radius loop below folds away; -1: taken from the launch parameters (any configuration).
+// Each thread loads only the rows its largest radius needs (RMIN rows either side for the min pools, RMAX for the max pools).
 template <int R, bool BORDER, int MINM, int MAXM>
-__device__ __forceinline__ void pass1(const FastParams& p, const float* s_z, float* s_V, int tid, int gy0, int gx0) {
+__device__ __forceinline__ void pass1(const FastParams& p, const float* s_z, float* s_V, int j, int seg, int gy0, int gx0) {
     constexpr int ZW = PW + 2 * R, ZP = ZW + 4;
     constexpr int NV = LV + 2 * R;
+    constexpr bool SPEC = MINM >= 0;
     const float INF = __int_as_float(0x7f800000);
-    const unsigned min_mask = MINM >= 0 ? (unsigned)MINM : p.ps.min_mask, max_mask = MAXM >= 0 ? (unsigned)MAXM : p.ps.max_mask;
-    const int n_min = MINM >= 0 ? cpopc((unsigned)(MINM >= 0 ? MINM : 0)) : p.ps.n_min;
-    for (int it = tid; it < ZW * (PHV / LV); it += NT) {
-        const int seg = it / ZW, j = it - seg * ZW;
-        const int rbase = seg * LV;
-        float f[NV];
+    const unsigned min_mask = SPEC ? (unsigned)MINM : p.ps.min_mask, max_mask = SPEC ? (unsigned)MAXM : p.ps.max_mask;
+    const int n_min = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) : p.ps.n_min;
+    constexpr int RA = SPEC ? (top_bit((unsigned)(SPEC ? MINM : 0)) > top_bit((unsigned)(SPEC ? MAXM : 0)) ? top_bit((unsigned)(SPEC ? MINM : 0))
+                                                                                                       : top_bit((unsigned)(SPEC ? MAXM : 0)))
+                            : R;   // largest radius actually used
+    const int rbase = seg * LV;
+    float f[NV];
+    const float* src = s_z + rbase * ZP + j + 2;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) f[i] = s_z[(rbase + i) * ZP + j + 2];
-        bool colin = true;
-        if (BORDER) colin = (unsigned)(gx0 + j) < (unsigned)p.W;
-        float* vdst = s_V + rbase * ZW + j;
-        if (min_mask) {
-            float g[NV], m[LV];
+    for (int i = R - RA; i < NV - (R - RA); ++i) f[i] = src[i * ZP];
+    bool colin = true;
+    if (BORDER) colin = (unsigned)(gx0 + j) < (unsigned)p.W;
+    float* vdst = s_V + rbase * ZW + j;
+    if (min_mask) {
+        constexpr int RM = SPEC ? top_bit((unsigned)(SPEC ? MINM : 0)) : R;
+        float g[NV], m[LV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                g[i] = (f[i] == 0.f) ? 999.f : f[i];
-                if (BORDER) g[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? g[i] : INF;
-            }
+        for (int i = R - RM; i < NV - (R - RM); ++i) {
+            g[i] = (f[i] == 0.f) ? 999.f : f[i];
+            if (BORDER) g[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? g[i] : INF;
+        }
 #pragma unroll
-            for (int i = 0; i < LV; ++i) m[i] = g[R + i];
+        for (int i = 0; i < LV; ++i) m[i] = g[R + i];
 #pragma unroll
-            for (int r = 1; r <= R; ++r) {
-                if ((min_mask >> r) != 0u) {  // some min pool has radius >= r
+        for (int r = 1; r <= RM; ++r) {
+            if ((min_mask >> r) != 0u) {  // some min pool has radius >= r
 #pragma unroll
-                    for (int i = 0; i < LV; ++i) m[i] = min_nan(m[i], min_nan(g[R + i - r], g[R + i + r]));
-                    if ((min_mask >> r) & 1u) {
-                        float* dst = vdst + __popc(min_mask & ((1u << r) - 1u)) * (PHV * ZW);
+                for (int i = 0; i < LV; ++i) m[i] = min_nan(m[i], min_nan(g[R + i - r], g[R + i + r]));
+                if ((min_mask >> r) & 1u) {
+                    float* dst = vdst + __popc(min_mask & ((1u << r) - 1u)) * (PH * ZW);
 #pragma unroll
-                        for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
-                    }
+                    for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
                 }
             }
         }
-        if (max_mask) {
-            float m[LV];
-            if (BORDER) {
+    }
+    if (max_mask) {
+        constexpr int RX = SPEC ? top_bit((unsigned)(SPEC ? MAXM : 0)) : R;
+        float m[LV];
+        if (BORDER) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i) f[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? f[i] : -INF;
-            }
+            for (int i = R - RX; i < NV - (R - RX); ++i) f[i] = (colin && (unsigned)(gy0 + rbase + i) < (unsigned)p.H) ? f[i] : -INF;
+        }
 #pragma unroll
-            for (int i = 0; i < LV; ++i) m[i] = f[R + i];
+        for (int i = 0; i < LV; ++i) m[i] = f[R + i];
 #pragma unroll
-            for (int r = 1; r <= R; ++r) {
-                if ((max_mask >> r) != 0u) {
+        for (int r = 1; r <= RX; ++r) {
+            if ((max_mask >> r) != 0u) {
 #pragma unroll
-                    for (int i = 0; i < LV; ++i) m[i] = max_nan(m[i], max_nan(f[R + i - r], f[R + i + r]));
-                    if ((max_mask >> r) & 1u) {
-                        float* dst = vdst + (n_min + __popc(max_mask & ((1u << r) - 1u))) * (PHV * ZW);
+                for (int i = 0; i < LV; ++i) m[i] = max_nan(m[i], max_nan(f[R + i - r], f[R + i + r]));
+                if ((max_mask >> r) & 1u) {
+                    float* dst = vdst + (n_min + __popc(max_mask & ((1u << r) - 1u))) * (PH * ZW);
 #pragma unroll
-                        for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
-                    }
+                    for (int i = 0; i < LV; ++i) dst[i * ZW] = m[i];
                 }
             }
         }
@@ -319,18 +328,151 @@ __device__ __forceinline__ void hwindow(const float (&v)[LH + 2 * R], int rk, fl
 #undef KB_STEP
 }
 
-template <int R, int MINM, int MAXM, int NCONV, int CIN>
+// one pool plane with a compile-time radius: only the 16-byte groups of the V row that the window touches are loaded
+template <int R, int RK, bool IS_MIN>
+__device__ __forceinline__ void hwindow_ct(const float* __restrict__ src, float (&m)[LH]) {
+    constexpr int LO = (R - RK) & ~3, HI = (R + LH + RK + 3) & ~3, NVV = HI - LO, C = R - LO;   // pixel i is v[C + i]
+    float v[NVV];
+#pragma unroll
+    for (int q = 0; q < NVV / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(src + LO + 4 * q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < LH; ++i) m[i] = v[C + i];
+#pragma unroll
+    for (int r = 1; r <= RK; ++r) {
+#pragma unroll
+        for (int i = 0; i < LH; ++i)
+            m[i] = IS_MIN ? min_nan(m[i], min_nan(v[C + i - r], v[C + i + r])) : max_nan(m[i], max_nan(v[C + i - r], v[C + i + r]));
+    }
+}
+
+// ---- C. pass 2 (horizontal) -> pyramid -> 1x1 chain -> Q chunk planes, one 4-pixel strip per thread -----------------------
+template <int R, int MINM, int MAXM, int NCONV, bool BORDER, bool PYR>
+__device__ __forceinline__ void pass2(const FastParams& p, const float* __restrict__ s_V, const float* __restrict__ s_w1, uint4* s_qhi,
+                                      uint4* s_qlo, int s, int n, int x0, int y0, int np, int n_conv) {
+    constexpr int ZW = PW + 2 * R;
+    constexpr bool SPEC = MINM >= 0;
+    constexpr int NS = PW / LH;
+    const float slope = p.slope;
+    const int n_min = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) : p.ps.n_min;
+    const int pr = s / NS, c0 = (s - pr * NS) * LH;
+    const int gy = y0 - 1 + pr, gxb = x0 - 2 + c0;
+    const int H = p.H, W = p.W;
+    const bool want_pyr = PYR && pr >= 1 && pr <= TH && gy < H;
+    u64 acc[NF][2];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[j][0] = acc[j][1] = 0ull;
+    const float* vrow = s_V + pr * ZW + c0;
+    // (999 -> 0) -> optional pyramid output -> first 1x1 layer
+    auto consume = [&](int k, bool is_min, float (&m)[LH]) {
+        if (is_min) {
+#pragma unroll
+            for (int i = 0; i < LH; ++i) m[i] = (m[i] == 999.f) ? 0.f : m[i];
+        }
+        if (PYR && want_pyr) {
+            float* dst = p.pyramid + ((size_t)n * np + p.ps.chan[k]) * ((size_t)H * W) + (size_t)gy * W;
+#pragma unroll
+            for (int i = 0; i < LH; ++i) {
+                const int c = c0 + i, gx = gxb + i;
+                if (c >= 2 && c < TW + 2 && gx < W) dst[gx] = m[i];
+            }
+        }
+        const u64 m01 = pack2(m[0], m[1]), m23 = pack2(m[2], m[3]);
+        const float4* wk = reinterpret_cast<const float4*>(s_w1 + k * NF);
+        const float4 wa = wk[0], wb = wk[1];
+        const float w[NF] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            acc[j][0] = ffma2s(w[j], m01, acc[j][0]);
+            acc[j][1] = ffma2s(w[j], m23, acc[j][1]);
+        }
+    };
+    if (SPEC) {
+        constexpr unsigned MM = SPEC ? (unsigned)MINM : 0u, XM = SPEC ? (unsigned)MAXM : 0u;
+        constexpr int NMIN = cpopc(MM), NMAX = cpopc(XM);
+        // explicit unrolling over the (at most 5 + 5) planes: the radius must be a template argument
+#define KB_PLANE(K)                                                                                        \
+        if (K < NMIN) { float m[LH]; hwindow_ct<R, nth_bit(MM, K < NMIN ? K : 0), true>(vrow + K * (PH * ZW), m); consume(K, true, m); }
+        KB_PLANE(0) KB_PLANE(1) KB_PLANE(2) KB_PLANE(3) KB_PLANE(4) KB_PLANE(5) KB_PLANE(6) KB_PLANE(7)
+#undef KB_PLANE
+#define KB_PLANE(K)                                                                                        \
+        if (K < NMAX) { float m[LH]; hwindow_ct<R, nth_bit(XM, K < NMAX ? K : 0), false>(vrow + (NMIN + K) * (PH * ZW), m); consume(NMIN + K, false, m); }
+        KB_PLANE(0) KB_PLANE(1) KB_PLANE(2) KB_PLANE(3) KB_PLANE(4) KB_PLANE(5) KB_PLANE(6) KB_PLANE(7)
+#undef KB_PLANE
+    } else {
+        for (int k = 0; k < np; ++k) {
+            const float* src = vrow + k * (PH * ZW);
+            float v[LH + 2 * R], m[LH];
+#pragma unroll
+            for (int q = 0; q < (LH + 2 * R) / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            if (k < n_min) hwindow<R, true>(v, p.ps.radius[k], m);
+            else           hwindow<R, false>(v, p.ps.radius[k], m);
+            consume(k, k < n_min, m);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(acc[j][0], slope); acc[j][1] = leaky01x2(acc[j][1], slope); }
+
+#pragma unroll 1
+    for (int l = 1; l < n_conv; ++l) {
+        const float4* wl = reinterpret_cast<const float4*>(s_w1 + NF * np + (l - 1) * NF * NF);
+        u64 nxt[NF][2];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) {
+            const float4 wa = wl[2 * k], wb = wl[2 * k + 1];
+            const float w[NF] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+                if (k == 0) {
+                    nxt[j][0] = fmul2s(w[j], acc[0][0]);
+                    nxt[j][1] = fmul2s(w[j], acc[0][1]);
+                } else {
+                    nxt[j][0] = ffma2s(w[j], acc[k][0], nxt[j][0]);
+                    nxt[j][1] = ffma2s(w[j], acc[k][1], nxt[j][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(nxt[j][0], slope); acc[j][1] = leaky01x2(nxt[j][1], slope); }
+    }
+    // Q -> bf16 hi/lo chunk planes; pixels outside the image are the zero padding of the 3x3 conv
+    float q[NF][LH];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) { unpack2(acc[j][0], q[j][0], q[j][1]); unpack2(acc[j][1], q[j][2], q[j][3]); }
+    const bool row_in = (unsigned)gy < (unsigned)H;
+#pragma unroll
+    for (int i = 0; i < LH; ++i) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) split_trunc(q[2 * jp][i], q[2 * jp + 1][i], hi[jp], lo[jp]);
+        if (BORDER) {
+            const bool inb = row_in && (unsigned)(gxb + i) < (unsigned)W;
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) { hi[jp] = inb ? hi[jp] : 0u; lo[jp] = inb ? lo[jp] : 0u; }
+        }
+        s_qhi[pr * PW + c0 + i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        s_qlo[pr * PW + c0 + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+template <int R, int MINM, int MAXM, int NCONV, int CIN, bool PYR>
 __global__ void __launch_bounds__(NT, 2)
 s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_x1) {
-    constexpr int ZW = PW + 2 * R, ZH = PHV + 2 * R, ZP = ZW + 4;
+    constexpr int ZW = PW + 2 * R, ZH = PH + 2 * R, ZP = ZW + 4;
     constexpr bool SPEC = MINM >= 0;  // pool sizes, n_convolution and input_channels are compile-time constants
     extern __shared__ __align__(128) uint8_t smem[];
     const int np = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) + cpopc((unsigned)(SPEC ? MAXM : 0)) : p.ps.n_pool;
     const int n_conv = SPEC ? NCONV : p.n_conv;
     const Layout L = make_layout(R, np, n_conv);
-    float* s_w1d = reinterpret_cast<float*>(smem + L.w1d);
+    float* s_w1 = reinterpret_cast<float*>(smem + L.w1);
     uint2* s_wB = reinterpret_cast<uint2*>(smem + L.wB);
-    uint2* s_xc = reinterpret_cast<uint2*>(smem + L.xc);
+    uint32_t* s_xch = reinterpret_cast<uint32_t*>(smem + L.xch);   // [row][XCP] pairs (hi[c], hi[c + 8])
+    uint32_t* s_xcl = reinterpret_cast<uint32_t*>(smem + L.xcl);   // [row][XCP] pairs (lo[c], lo[c + 8])
     float* s_V = reinterpret_cast<float*>(smem + L.v);
     float* s_z = reinterpret_cast<float*>(smem + L.z);
     float* s_x1 = reinterpret_cast<float*>(smem + L.x1);
@@ -339,12 +481,8 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     const uint32_t bar = smem_u32(smem);
 
     const int tid = threadIdx.x;
-    int b = blockIdx.x;
-    const int tx = b % p.tiles_x;
-    b /= p.tiles_x;
-    const int ty = b % p.tiles_y;
-    const int n = b / p.tiles_y;
-    const int x0 = tx * TW, y0 = ty * TH;
+    const int n = blockIdx.z;                       // 3-D grid: no index arithmetic (two integer divisions were ~7 % of the kernel)
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int H = p.H, W = p.W;
     const size_t plane = (size_t)H * W;
     const int gy0 = y0 - 1 - R, gx0 = x0 - 2 - R;  // image coordinates of logical z-tile element (0, 0) (smem column 2)
@@ -353,7 +491,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
 
     // ---- A. stage the input tile and the weights ---------------------------------------------------------------------
     const bool bulk_w = p.wpack != nullptr;
-    const uint32_t wbytes = (uint32_t)(w1d_bytes(np, n_conv) + WB_BYTES);
+    const uint32_t wbytes = (uint32_t)(w1_bytes(np, n_conv) + WB_BYTES);
     if (tid == 0 && (p.use_tma || bulk_w)) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -365,7 +503,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             tma_load_3d(smem_u32(s_z), &tm_z, gx0 - 2, gy0, n * C_in, bar);
             if (C_in > 1) tma_load_3d(smem_u32(s_x1), &tm_x1, x0 - 4, y0 - 1, n * C_in + 1, bar);
         }
-        if (bulk_w) bulk_g2s(smem_u32(s_w1d), p.wpack, wbytes, bar);
+        if (bulk_w) bulk_g2s(smem_u32(s_w1), p.wpack, wbytes, bar);
     }
     if (!p.use_tma) {  // shapes the tensor map cannot describe (W % 4 != 0, unaligned base): plain loads, same smem image
         const float* xin = p.x + (size_t)n * C_in * plane;
@@ -381,24 +519,44 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
                 s_x1[idx] = ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) ? __ldg(xin + plane + (size_t)gy * W + gx) : 0.f;
             }
     }
-    if (!bulk_w) build_weight_image(p.ws, smem + L.w1d, tid, NT);
+    if (!bulk_w) build_weight_image(p.ws, smem + L.w1, tid, NT);
     __syncthreads();
     if (p.use_tma || bulk_w) mbar_wait(bar, 0);
 
-    // ---- B. pass 1 (vertical) + raw-channel split -------------------------------------------------------------------
+    // ---- B. pass 1 (vertical): the first warps own one (column, 7-row segment) each; the remaining warps split the raw
+    //         channels of the 3x3 conv input to packed bf16 -------------------------------------------------------------
+    const bool border = gy0 < 0 || gx0 < 0 || gy0 + ZH > H || gx0 + ZW > W;
     {
-        const bool border = gy0 < 0 || gx0 < 0 || gy0 + ZH > H || gx0 + ZW > W;
-        if (border) pass1<R, true, MINM, MAXM>(p, s_z, s_V, tid, gy0, gx0);
-        else        pass1<R, false, MINM, MAXM>(p, s_z, s_V, tid, gy0, gx0);
-        // raw channels of the 3x3 conv input as packed bf16: .x = hi pair, .y = lo pair.
-        //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
-        for (int idx = tid; idx < PH * PW; idx += NT) {
-            const int pr = idx / PW, c = idx - pr * PW;
-            const float a = s_z[(pr + R) * ZP + c + R + 2];
-            const float bb = C_in > 1 ? s_x1[pr * XP + c + 2] : s_z[(pr + R) * ZP + c + R + 3];
-            uint32_t hi, lo;
-            split_rn(a, bb, hi, lo);
-            s_xc[idx] = make_uint2(hi, lo);
+        constexpr int N_P1 = 2 * ZW;                       // work items of pass 1
+        constexpr int T_P1 = ((N_P1 + 31) / 32) * 32;      // ... rounded up to whole warps
+        static_assert(T_P1 < NT, "pass 1 leaves no warp for the raw-channel split");
+        if (tid < T_P1) {
+            if (tid < N_P1) {
+                const int seg = tid >= ZW ? 1 : 0, j = tid - seg * ZW;
+                if (border) pass1<R, true, MINM, MAXM>(p, s_z, s_V, j, seg, gy0, gx0);
+                else        pass1<R, false, MINM, MAXM>(p, s_z, s_V, j, seg, gy0, gx0);
+            }
+        } else {
+            // raw channels of the 3x3 conv input as packed bf16 words (two k-slots each):
+            //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
+            // stored as 8-byte entries (word[c], word[c + 8]) -- the two pixel halves of an mma A fragment -- so that one
+            // LDS.64 fills two consecutive fragment registers.  Entry PW of every row is zero: k-slots that carry no raw
+            // channel read it.
+            constexpr int STEP = NT - T_P1;
+            int idx = tid - T_P1, pr = idx / XCP, c = idx - pr * XCP;
+            for (; idx < PH * XCP; idx += STEP, c += STEP % XCP, pr += STEP / XCP) {
+                if (c >= XCP) { c -= XCP; ++pr; }
+                uint32_t hi = 0u, lo = 0u;
+                if (c < PW) {
+                    const float a = s_z[(pr + R) * ZP + c + R + 2];
+                    const float bb = C_in > 1 ? s_x1[pr * XP + c + 2] : s_z[(pr + R) * ZP + c + R + 3];
+                    split_rn(a, bb, hi, lo);
+                }
+                s_xch[2 * idx] = hi;
+                s_xcl[2 * idx] = lo;
+                if (c >= 8 && c < PW) { s_xch[2 * (idx - 8) + 1] = hi; s_xcl[2 * (idx - 8) + 1] = lo; }
+                if (c >= PW - 8) { s_xch[2 * idx + 1] = 0u; s_xcl[2 * idx + 1] = 0u; }
+            }
         }
     }
     __syncthreads();
@@ -406,111 +564,16 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     // ---- C. pass 2 (horizontal) -> pyramid -> 1x1 chain -> Q chunk planes ----------------------------------------------
     {
         constexpr int NS = PW / LH;
-        const u64 slope2 = pack2(slope, slope);
-        const int n_min = SPEC ? cpopc((unsigned)(SPEC ? MINM : 0)) : p.ps.n_min;
-        for (int s = tid; s < PH * NS; s += NT) {
-            const int pr = s / NS, c0 = (s - pr * NS) * LH;
-            const int gy = y0 - 1 + pr, gxb = x0 - 2 + c0;
-            const bool want_pyr = p.pyramid != nullptr && pr >= 1 && pr <= TH && gy < H;
-            u64 acc[NF][2];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) acc[j][0] = acc[j][1] = 0ull;
-            // one pool plane: horizontal window -> (999 -> 0) -> optional pyramid output -> first 1x1 layer
-            auto pool_plane = [&](int k, int rk, bool is_min) {
-                const float* src = s_V + (k * PHV + pr) * ZW + c0;
-                float v[LH + 2 * R], m[LH];
-#pragma unroll
-                for (int q = 0; q < (LH + 2 * R) / 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-                }
-                if (is_min) {
-                    hwindow<R, true>(v, rk, m);
-#pragma unroll
-                    for (int i = 0; i < LH; ++i) m[i] = (m[i] == 999.f) ? 0.f : m[i];
-                } else {
-                    hwindow<R, false>(v, rk, m);
-                }
-                if (want_pyr) {
-                    float* dst = p.pyramid + ((size_t)n * np + p.ps.chan[k]) * plane + (size_t)gy * W;
-#pragma unroll
-                    for (int i = 0; i < LH; ++i) {
-                        const int c = c0 + i, gx = gxb + i;
-                        if (c >= 2 && c < TW + 2 && gx < W) dst[gx] = m[i];
-                    }
-                }
-                const u64 m01 = pack2(m[0], m[1]), m23 = pack2(m[2], m[3]);
-                const ulonglong2* wk = reinterpret_cast<const ulonglong2*>(s_w1d + (size_t)k * NF * 2);
-#pragma unroll
-                for (int jj = 0; jj < NF / 2; ++jj) {
-                    const ulonglong2 w2 = wk[jj];
-                    acc[2 * jj][0] = ffma2(w2.x, m01, acc[2 * jj][0]);
-                    acc[2 * jj][1] = ffma2(w2.x, m23, acc[2 * jj][1]);
-                    acc[2 * jj + 1][0] = ffma2(w2.y, m01, acc[2 * jj + 1][0]);
-                    acc[2 * jj + 1][1] = ffma2(w2.y, m23, acc[2 * jj + 1][1]);
-                }
-            };
-            if (SPEC) {
-                constexpr unsigned MM = SPEC ? (unsigned)MINM : 0u, XM = SPEC ? (unsigned)MAXM : 0u;
-                constexpr int NMIN = cpopc(MM), NMAX = cpopc(XM);
-#pragma unroll
-                for (int k = 0; k < NMIN; ++k) pool_plane(k, nth_bit(MM, k), true);
-#pragma unroll
-                for (int k = 0; k < NMAX; ++k) pool_plane(NMIN + k, nth_bit(XM, k), false);
-            } else {
-                for (int k = 0; k < np; ++k) pool_plane(k, p.ps.radius[k], k < n_min);
-            }
-#pragma unroll
-            for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(acc[j][0], slope2); acc[j][1] = leaky01x2(acc[j][1], slope2); }
-
-            for (int l = 1; l < n_conv; ++l) {
-                const ulonglong2* wl = reinterpret_cast<const ulonglong2*>(s_w1d + (size_t)(NF * np + (l - 1) * NF * NF) * 2);
-                u64 nxt[NF][2];
-#pragma unroll
-                for (int k = 0; k < NF; ++k) {
-#pragma unroll
-                    for (int jj = 0; jj < NF / 2; ++jj) {
-                        const ulonglong2 w2 = wl[k * (NF / 2) + jj];
-                        if (k == 0) {
-                            nxt[2 * jj][0] = fmul2(w2.x, acc[0][0]);
-                            nxt[2 * jj][1] = fmul2(w2.x, acc[0][1]);
-                            nxt[2 * jj + 1][0] = fmul2(w2.y, acc[0][0]);
-                            nxt[2 * jj + 1][1] = fmul2(w2.y, acc[0][1]);
-                        } else {
-                            nxt[2 * jj][0] = ffma2(w2.x, acc[k][0], nxt[2 * jj][0]);
-                            nxt[2 * jj][1] = ffma2(w2.x, acc[k][1], nxt[2 * jj][1]);
-                            nxt[2 * jj + 1][0] = ffma2(w2.y, acc[k][0], nxt[2 * jj + 1][0]);
-                            nxt[2 * jj + 1][1] = ffma2(w2.y, acc[k][1], nxt[2 * jj + 1][1]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < NF; ++j) { acc[j][0] = leaky01x2(nxt[j][0], slope2); acc[j][1] = leaky01x2(nxt[j][1], slope2); }
-            }
-            // Q -> bf16 hi/lo chunk planes; pixels outside the image are the zero padding of the 3x3 conv
-            float q[NF][LH];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) { unpack2(acc[j][0], q[j][0], q[j][1]); unpack2(acc[j][1], q[j][2], q[j][3]); }
-            const bool row_in = (unsigned)gy < (unsigned)H;
-#pragma unroll
-            for (int i = 0; i < LH; ++i) {
-                const bool inb = row_in && (unsigned)(gxb + i) < (unsigned)W;
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int jp = 0; jp < 4; ++jp) {
-                    split_trunc(q[2 * jp][i], q[2 * jp + 1][i], hi[jp], lo[jp]);
-                    hi[jp] = inb ? hi[jp] : 0u;
-                    lo[jp] = inb ? lo[jp] : 0u;
-                }
-                s_qhi[pr * PW + c0 + i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                s_qlo[pr * PW + c0 + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
+        static_assert(PH * NS <= NT, "one strip per thread");
+        if (tid < PH * NS) {
+            if (border) pass2<R, MINM, MAXM, NCONV, true, PYR>(p, s_V, s_w1, s_qhi, s_qlo, tid, n, x0, y0, np, n_conv);
+            else        pass2<R, MINM, MAXM, NCONV, false, PYR>(p, s_V, s_w1, s_qhi, s_qlo, tid, n, x0, y0, np, n_conv);
         }
     }
     __syncthreads();
 
     // ---- D. 3x3 conv on mma.sync (bf16 x3 split), LeakyReLU, NCHW stores ---------------------------------------------
-    {
+    if (tid < CONV_WARPS * 32) {
         const int warp = tid >> 5, lane = tid & 31;
         constexpr int LR = TH / 2;                 // output rows per warp
         const int cb = warp & 3, rg = warp >> 2;  // 16-column block, row group
@@ -528,16 +591,16 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         const int mrow = ((lane >> 3) & 1) * 8 + (lane & 7);
         const int col_s0 = 16 * cb + mrow + 1 + (lane >> 4);  // k-step half 0: dx = 0 (chunk A), dx = 1 (chunk B)
         const int col_s1 = 16 * cb + mrow + 1 + 2;            // k-step half 1, chunk A: dx = 2
-        // raw-channel fragment: lane t holds slots (2t, 2t+1)
-        int xoff;
-        uint32_t xmask;
-        if (C_in > 1) { xoff = t < 3 ? t : 0; xmask = t < 3 ? 0xFFFFFFFFu : 0u; }
-        else          { xoff = t < 2 ? 2 * t : 0; xmask = t == 0 ? 0xFFFFFFFFu : (t == 1 ? 0x0000FFFFu : 0u); }
-        const int col_x = 16 * cb + g + 1 + xoff;
+        // raw-channel fragment: lane t holds slots (2t, 2t+1); a lane whose slots carry nothing reads the zero entry of the row
+        int col_x;
+        uint32_t xmask = 0xFFFFFFFFu;
+        if (C_in > 1) { col_x = t < 3 ? 16 * cb + g + 1 + t : PW; }
+        else          { col_x = t < 2 ? 16 * cb + g + 1 + 2 * t : PW; xmask = t == 1 ? 0x0000FFFFu : 0xFFFFFFFFu; }
         const uint32_t q_row0 = (uint32_t)(LR * rg * PW) * 16u;
         const uint32_t a_s0h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s0 * 16u, a_s0l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s0 * 16u;
         const uint32_t a_s1h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s1 * 16u, a_s1l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s1 * 16u;
-        const uint2* xrow = s_xc + LR * rg * PW + col_x;
+        const uint2* xrow_h = reinterpret_cast<const uint2*>(s_xch) + LR * rg * XCP + col_x;
+        const uint2* xrow_l = reinterpret_cast<const uint2*>(s_xcl) + LR * rg * XCP + col_x;
 #pragma unroll
         for (int qr = 0; qr < LR + 2; ++qr) {
             uint32_t a0h[4], a0l[4], a1h[4], a1l[4];
@@ -545,9 +608,9 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             ldsm_x4(a_s0l + (uint32_t)(qr * PW * 16), a0l);
             ldsm_x2(a_s1h + (uint32_t)(qr * PW * 16), a1h[0], a1h[1]);
             ldsm_x2(a_s1l + (uint32_t)(qr * PW * 16), a1l[0], a1l[1]);
-            const uint2 xa = xrow[qr * PW], xb = xrow[qr * PW + 8];
-            a1h[2] = xa.x & xmask; a1l[2] = xa.y & xmask;
-            a1h[3] = xb.x & xmask; a1l[3] = xb.y & xmask;
+            const uint2 xh = xrow_h[qr * XCP], xl = xrow_l[qr * XCP];
+            if (C_in > 1) { a1h[2] = xh.x; a1h[3] = xh.y; a1l[2] = xl.x; a1l[3] = xl.y; }
+            else          { a1h[2] = xh.x & xmask; a1h[3] = xh.y & xmask; a1l[2] = xl.x & xmask; a1l[3] = xl.y & xmask; }
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
                 const int li = qr - dy;
@@ -563,15 +626,27 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         }
         // epilogue: c0,c1 = (pixel g, filters 2t, 2t+1), c2,c3 = (pixel g + 8, same filters)
         const int gxa = x0 + 16 * cb + g;
-        const bool in_a = gxa < W, in_b = gxa + 8 < W;
         float* d0 = p.out + ((size_t)n * NF + 2 * t) * plane + (size_t)(y0 + LR * rg) * W + gxa;
+        float* d1 = d0 + plane;
+        if (y0 + TH <= H && x0 + TW <= W) {           // full tile (every tile of the shipped shapes): no bounds checks
 #pragma unroll
-        for (int li = 0; li < LR; ++li) {
-            if (y0 + LR * rg + li < H) {
-                if (in_a) { d0[0] = leaky01(acc[li][0], slope); d0[plane] = leaky01(acc[li][1], slope); }
-                if (in_b) { d0[8] = leaky01(acc[li][2], slope); d0[plane + 8] = leaky01(acc[li][3], slope); }
+            for (int li = 0; li < LR; ++li) {
+                float v0, v1, v2, v3;
+                unpack2(leaky01x2(pack2(acc[li][0], acc[li][1]), slope), v0, v1);
+                unpack2(leaky01x2(pack2(acc[li][2], acc[li][3]), slope), v2, v3);
+                d0[0] = v0; d1[0] = v1; d0[8] = v2; d1[8] = v3;
+                d0 += W; d1 += W;
             }
-            d0 += W;
+        } else {
+            const bool in_a = gxa < W, in_b = gxa + 8 < W;
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                if (y0 + LR * rg + li < H) {
+                    if (in_a) { d0[0] = leaky01(acc[li][0], slope); d1[0] = leaky01(acc[li][1], slope); }
+                    if (in_b) { d0[8] = leaky01(acc[li][2], slope); d1[8] = leaky01(acc[li][3], slope); }
+                }
+                d0 += W; d1 += W;
+            }
         }
     }
 }
@@ -605,25 +680,30 @@ bool make_map(CUtensorMap* tm, const float* x, int NC, int H, int W, int bw, int
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, int MINM = -1, int MAXM = -1, int NCONV = 0, int CIN = 0>
-int launch_fast(FastParams& p, cudaStream_t stream) {
+template <int R, int MINM, int MAXM, int NCONV, int CIN, bool PYR>
+int launch_fast_t(FastParams& p, cudaStream_t stream) {
     const Layout L = make_layout(R, p.ps.n_pool, p.n_conv);
     alignas(64) CUtensorMap tm_z, tm_x1;
     memset(&tm_z, 0, sizeof(tm_z));
     memset(&tm_x1, 0, sizeof(tm_x1));
     static const bool no_tma = getenv("KBNET_S2D_NO_TMA") != nullptr;  // debugging aid: stage the tile with plain loads
-    p.use_tma = !no_tma && make_map(&tm_z, p.x, p.N * p.C_in, p.H, p.W, PW + 2 * R + 4, PHV + 2 * R) &&
+    p.use_tma = !no_tma && make_map(&tm_z, p.x, p.N * p.C_in, p.H, p.W, PW + 2 * R + 4, PH + 2 * R) &&
                 (p.C_in == 1 || make_map(&tm_x1, p.x, p.N * p.C_in, p.H, p.W, XP, PH));
-    auto kern = s2d_fused_kernel<R, MINM, MAXM, NCONV, CIN>;
+    auto kern = s2d_fused_kernel<R, MINM, MAXM, NCONV, CIN, PYR>;
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     p.tiles_x = cdiv(p.W, TW);
     p.tiles_y = cdiv(p.H, TH);
-    const long long grid = (long long)p.tiles_x * p.tiles_y * p.N;
-    KB_CHECK_ARG(grid > 0 && grid < (1ll << 31), "s2d: grid too large");
-    kern<<<(unsigned)grid, NT, L.total, stream>>>(p, tm_z, tm_x1);
+    KB_CHECK_ARG(p.tiles_y <= 65535 && p.N <= 65535, "s2d: more than 65535 tile rows or samples in one launch");
+    kern<<<dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)p.N), NT, L.total, stream>>>(p, tm_z, tm_x1);
     KB_CUDA(cudaGetLastError());
     count_launch();
     return 0;
+}
+
+// the pyramid output is a test / debugging facility: its stores live in a second instantiation of the kernel
+template <int R, int MINM = -1, int MAXM = -1, int NCONV = 0, int CIN = 0>
+int launch_fast(FastParams& p, cudaStream_t stream) {
+    return p.pyramid ? launch_fast_t<R, MINM, MAXM, NCONV, CIN, true>(p, stream) : launch_fast_t<R, MINM, MAXM, NCONV, CIN, false>(p, stream);
 }
 
 // canonical pool order; false if the configuration is outside the fast path (duplicate sizes within a group)
@@ -665,7 +745,7 @@ bool fast_path(int C_in, const int* min_sizes, int n_min, const int* max_sizes, 
     const int rmax = ps->rmax_min > ps->rmax_max ? ps->rmax_min : ps->rmax_max;
     const int R = rmax <= 4 ? 4 : (rmax <= 8 ? 8 : 16);
     *R_out = R;
-    return C_in >= 1 && C_in <= 2 && slope >= 0.f && slope <= 1.f && make_layout(R, ps->n_pool, n_conv).total <= SMEM_2CTA;
+    return C_in >= 1 && C_in <= 2 && slope >= 0.f && slope <= 1.f && make_layout(R, ps->n_pool, n_conv).total <= SMEM_MAX;
 }
 
 }  // namespace
@@ -674,7 +754,7 @@ size_t s2d_wpack_bytes(int C_in, const int* min_sizes, int n_min, const int* max
     PoolSpec ps;
     int R;
     if (!min_sizes || !max_sizes || !fast_path(C_in, min_sizes, n_min, max_sizes, n_max, n_conv, n_filter, slope, &ps, &R)) return 0;
-    return (size_t)w1d_bytes(ps.n_pool, n_conv) + WB_BYTES;
+    return (size_t)w1_bytes(ps.n_pool, n_conv) + WB_BYTES;
 }
 
 int s2d_pack_weights(const float* const* w_1x1, int n_conv, const float* w_3x3, int C_in, const int* min_sizes, int n_min,
