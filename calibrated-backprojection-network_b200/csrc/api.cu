@@ -202,6 +202,19 @@ int kbnet_conv3x3_depth_head_forward(const float* x, long long x_stride_n, int N
                              (cudaStream_t)stream);
 }
 
+/* 3x3 stride-1 convolutions with few channels on the warp-level tensor path (csrc/conv_mma.cu) */
+int kbnet_conv3x3_small_supported(int C, int F, int ksize, int stride) { return conv_mma_supported(C, F, ksize, stride) ? 1 : 0; }
+
+int kbnet_conv3x3_small_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
+                                float neg_slope, float* y, long long y_stride_n, void* stream) {
+    if (N == 0) return 0;
+    KB_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv3x3_small: bad argument");
+    KB_CHECK_ARG(conv_mma_supported(C, F, 3, 1), "conv3x3_small: C=%d F=%d unsupported (C <= 4 and F <= 48, or C <= 16 and F <= 16)", C, F);
+    KB_CHECK_ARG(act == 0 || (act == 1 && neg_slope >= 0.f && neg_slope <= 1.f), "conv3x3_small: act=%d neg_slope=%g unsupported", act, (double)neg_slope);
+    KB_CHECK_ARG(x_stride_n >= (long long)C * H * W && y_stride_n >= (long long)F * H * W, "conv3x3_small: stride_n too small");
+    return conv_mma_launch(x, x_stride_n, N, C, H, W, w, F, act, neg_slope, y, y_stride_n, (cudaStream_t)stream);
+}
+
 /* nearest-2x upsample + 3x3 conv as four source-resolution 2x2 convolutions (csrc/conv_tma.cu) */
 int kbnet_upconv2x_supported(const float* x, int C, int Hs, int Ws, long long stride_n, int F) {
     ConvSrcDev s = make_src(x, nullptr, C, Hs, Ws, stride_n, SRC_DIRECT);

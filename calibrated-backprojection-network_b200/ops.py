@@ -7,8 +7,12 @@ from . import _lib
 from .modules import _view4, _w, _stream, packed_weight
 
 
-def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None):
+def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
     """out = act(conv_k(cat_c(sources), weight)), padding k//2, no bias.
+
+    engine=None picks the kernel by shape: a single full-resolution source with few channels and filters (3x3, stride 1)
+    goes to the warp-level tensor kernel (kbnet_conv3x3_small_forward), everything else to the tcgen05 engine behind
+    kbnet_conv2d_forward; engine='tcgen05' forces the latter (used by the engine's own tests).
 
     sources: list of 4-D CUDA float32 tensors or ``(tensor, 'up')`` pairs; an ``'up'`` source is nearest-upsampled to
     the spatial size of the first non-upsampled source (or ``size`` given as ``(tensor, 'up', (H, W))``) inside the kernel.
@@ -43,10 +47,20 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None):
         out = torch.empty((n, f, ho, wo), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (n, f, ho, wo) or out.stride()[1:] != (ho * wo, wo, 1) or out.dtype != torch.float32:
         raise RuntimeError('kbnet_b200: bad preallocated conv output')
+    osn = out.stride(0) if n > 1 else f * ho * wo
+    from .modules import get_precision
+    if engine is None and len(parsed) == 1 and parsed[0][2] == 0 and get_precision() == 'bf16x3' and \
+            (slope is None or 0.0 <= float(slope) <= 1.0) and lib.kbnet_conv3x3_small_supported(ctot, f, k, stride) and \
+            not (f <= 4 and ctot <= 32):        # <= 4 filters: the exact-fp32 CUDA-core kernel inside kbnet_conv2d_forward
+        t, sn, _ = parsed[0]
+        with torch.cuda.device(dev):
+            rc = lib.kbnet_conv3x3_small_forward(t.data_ptr(), sn, n, ctot, h_in, w_in, w.data_ptr(), f, 0 if slope is None else 1,
+                                                 0.0 if slope is None else float(slope), out.data_ptr(), osn, _stream(dev))
+        _lib.check(rc, 'kbnet_conv3x3_small_forward')
+        return out
     arr = (_lib.KBNetConvSrc * len(parsed))()
     for i, (t, sn, mode) in enumerate(parsed):
         arr[i].ptr, arr[i].C, arr[i].H, arr[i].W, arr[i].stride_n, arr[i].mode = t.data_ptr(), t.shape[1], t.shape[2], t.shape[3], sn, mode
-    osn = out.stride(0) if n > 1 else f * ho * wo
     pk = packed_weight(weight, [t.shape[1] for t, _, _ in parsed])
     with torch.cuda.device(dev):
         rc = lib.kbnet_conv2d_forward(arr, len(parsed), n, h_in, w_in, w.data_ptr(), pk.data_ptr() if pk is not None else None,

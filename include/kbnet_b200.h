@@ -167,6 +167,16 @@ int kbnet_intrinsics_inverse(const float* K, int N, float scale_x, float scale_y
 int kbnet_conv3x3_depth_head_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F,
                                      double min_depth, double max_depth, float* y, long long y_stride_n, void* stream);
 
+/* Conv2d with a 3x3 kernel, stride 1 and FEW channels (C <= 4 and F <= 48, or C <= 16 and F <= 16): KBNet's full-resolution
+ * layers conv0_image 3 -> 48, conv0_depth 8 -> 16 (reference src/networks.py:364-365) and deconv0.conv 12 -> 12
+ * (src/net_utils.py:1482-1487).  y = act(conv3x3_pad1(x, w)); act = 0 linear, 1 LeakyReLU(neg_slope), 0 <= neg_slope <= 1.
+ * x [N,C,H,W] and y [N,F,H,W] fp32, either may be a channel slice of a wider NCHW buffer (*_stride_n).  Warp-level tensor
+ * path (mma.sync bf16, 3-term operand split, fp32 accumulate: ~1e-5 relative) -- with so few filters the tcgen05 engine
+ * behind kbnet_conv2d_forward is bound by its per-MMA issue cost.  kbnet_conv3x3_small_supported returns 1 for the shapes taken. */
+int kbnet_conv3x3_small_supported(int C, int F, int ksize, int stride);
+int kbnet_conv3x3_small_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
+                                float neg_slope, float* y, long long y_stride_n, void* stream);
+
 /* OutlierRemoval.remove_outliers (reference src/net_utils.py:1761-1806): drop sparse points that are more than `threshold`
  * behind the nearest point of their kernel_size x kernel_size neighbourhood.  sparse_depth / validity_map / outputs are
  * [N,1,H,W]; validity_map may be NULL, then it is derived as in src/kbnet.py:899-902 (depth > 0 ? 1 : depth).  The global

@@ -58,7 +58,7 @@ def test_tma_engine_vs_fp64(case):
     wt = torch.randn(f, sum(chans), k, k, generator=gen) / (sum(chans) * k * k) ** 0.5
     ref = _ref(srcs, wt, stride, 0.2)
     c0 = _v2_count()
-    got = kbnet_b200.ops.conv2d_fused([s.to(DEV) for s in srcs], wt.to(DEV), stride, 0.2)
+    got = kbnet_b200.ops.conv2d_fused([s.to(DEV) for s in srcs], wt.to(DEV), stride, 0.2, engine='tcgen05')
     assert _v2_count() == c0 + 1, 'the TMA engine did not take this shape'
     assert_close(got, ref, tol=1e-4, what=name)
 

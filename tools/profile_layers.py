@@ -5,7 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kbnet_b200
 import kbnet_b200.model as M
 from kbnet_b200 import ops, modules
-from bench import synth_inputs, MIN_POOLS, MAX_POOLS, F_IMG, F_DEP, F_DEC
+from bench import synth_inputs, WORKLOADS, F_IMG, F_DEP, F_DEC
+CFG = WORKLOADS['kitti']
+MIN_POOLS, MAX_POOLS = CFG['min_pools'], CFG['max_pools']
 
 torch.set_grad_enabled(False)
 if os.environ.get('KBNET_AUTOTUNE', '1') != '0':
@@ -13,7 +15,7 @@ if os.environ.get('KBNET_AUTOTUNE', '1') != '0':
 dev = torch.device('cuda:0')
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 model = kbnet_b200.KBNetModel(3, 2, MIN_POOLS, MAX_POOLS, 3, 8, F_IMG, F_DEP, [0, 1, 2, 3], F_DEC, device=dev)
-inp = [t.to(dev) for t in synth_inputs(N, 1)]
+inp = [t.to(dev) for t in synth_inputs(CFG, N, 1)]
 for _ in range(3):
     model.forward(*inp)
 torch.cuda.synchronize()
@@ -34,6 +36,7 @@ def timed(name_fn, fn):
 
 def conv_name(a, kw, y):
     srcs, w = a[0], a[1]
+    a = list(a) + [kw.get('stride', 1)] * 3
     desc = '+'.join(('up' if isinstance(s, (tuple, list)) else '') + str((s[0] if isinstance(s, (tuple, list)) else s).shape[1]) for s in srcs)
     flops = 2.0 * y.numel() * w.shape[1] * w.shape[2] * w.shape[3]
     return 'conv %dx%d s%d  %s -> %d @%dx%d' % (w.shape[2], w.shape[3], a[2], desc, w.shape[0], y.shape[2], y.shape[3]), flops
