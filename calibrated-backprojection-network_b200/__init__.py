@@ -5,11 +5,12 @@ Importable as ``kbnet_b200`` (see kbnet_b200.py at the repository root; this dir
 contract asks for).  The compute lives in libkbnet_b200.so (csrc/, C ABI in include/kbnet_b200.h).
 """
 from . import _lib, build as _build, dist, ops
-from .modules import CalibratedBackprojectionBlock, OutlierRemoval, SparseToDensePool, install, set_precision, get_precision
+from .modules import (CalibratedBackprojectionBlock, OutlierRemoval, SparseToDensePool, install, invalidate_packs, set_precision,
+                      get_precision)
 from .model import GraphRunner, KBNetEncoder, KBNetModel, MultiScaleDecoder
 
 __all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'OutlierRemoval', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
-           'install', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']
+           'install', 'invalidate_packs', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']
 
 
 def build_library(force=False, verbose=False):

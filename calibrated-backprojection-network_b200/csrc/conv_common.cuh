@@ -85,7 +85,8 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
                     float* out_image, long long out_image_sn, float* out_depth, long long out_depth_sn, float* out_fused, long long out_fused_sn,
                     cudaStream_t stream);
 inline int conv_launch(const ConvParams& p, const void* wpack, cudaStream_t stream) {
-    if (!wpack) return conv_direct_launch(p, stream);
+    // no packed weights (fp32 mode), or a layer outside both tensor-core envelopes: the exact-fp32 CUDA-core kernel
+    if (!wpack || (!conv_v2_supported(p) && !conv_umma_supported(p))) return conv_direct_launch(p, stream);
     return conv_v2_supported(p) ? conv_v2_launch(p, wpack, stream) : conv_umma_launch(p, wpack, stream);
 }
 int kb_proj_z_launch(const float* depth, long long stride_n, const float* w, int N, int C, int H, int W, int Ho, int Wo, float slope, float* z,

@@ -144,6 +144,7 @@ bool conv_small_supported(int C, int F, int ksize, int stride) { return ksize ==
 int conv_small_launch(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act, float slope, float head_min,
                       float head_ratio, float* out, long long out_stride_n, cudaStream_t stream) {
     KB_CHECK_ARG(conv_small_supported(C, F, 3, 1), "conv(small): C=%d F=%d unsupported", C, F);
+    KB_CHECK_ARG(N <= 65535 && cdiv(H, ST_H) <= 65535, "conv_small: more than 65535 samples or tile rows in one launch");
     dim3 grid(cdiv(W, ST_W), cdiv(H, ST_H), N);
     const size_t smem = (size_t)(C * F * 12 + C * PHt * PWd) * sizeof(float) + 16;  // sized for the real C: several CTAs per SM overlap load and math
     alignas(64) CUtensorMap tm;

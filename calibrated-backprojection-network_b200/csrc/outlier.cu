@@ -7,7 +7,9 @@
 //   keep      = !(m < sparse_depth - threshold)
 //   validity' = validity * keep ;  depth' = sparse_depth * validity'
 //
-// Pure selection / comparison arithmetic: bit-exact against ATen.  Two launches: a grid-stride max reduction (no host
+// Pure selection / comparison arithmetic: bit-exact against ATen for NaN-free inputs (the sliding minimum propagates NaN like
+// ATen's max_pool2d does; the reference's global torch.max turns the WHOLE batch into NaN when one value is NaN, which this
+// kernel's ordered-integer maximum does not reproduce -- NaN depths are outside the reference's own data contract).  Two launches: a grid-stride max reduction (no host
 // synchronisation, unlike the reference's `full_like(fill_value=tensor)` which reads the maximum back), then one fused
 // tile kernel (separable sliding minimum in shared memory).
 #include "conv_common.cuh"
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) outlier_kernel(const float* __restrict__ 
         const int ty = i / OT, tx = i - ty * OT;
         const float* row = s_f + ty * TWH + tx;
         float m = row[0];
-        for (int k = 1; k <= 2 * r; ++k) m = fminf(m, row[k]);
+        for (int k = 1; k <= 2 * r; ++k) m = min_nan(m, row[k]);
         s_h[i] = m;
     }
     __syncthreads();
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) outlier_kernel(const float* __restrict__ 
         const int gy = y0 + ty, gx = x0 + tx;
         if (gy >= H || gx >= W) continue;
         float m = s_h[ty * OT + tx];
-        for (int k = 1; k <= 2 * r; ++k) m = fminf(m, s_h[(ty + k) * OT + tx]);
+        for (int k = 1; k <= 2 * r; ++k) m = min_nan(m, s_h[(ty + k) * OT + tx]);
         const size_t o = (size_t)n * plane + (size_t)gy * W + gx;
         const float z = __ldg(depth + o);
         const float val = validity ? __ldg(validity + o) : (z > 0.f ? 1.f : z);
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(256) outlier_kernel(const float* __restrict__ 
 int outlier_removal_launch(const float* depth, const float* validity, int N, int H, int W, int ksize, float threshold, float* out_depth,
                            float* out_valid, void* workspace, cudaStream_t stream) {
     KB_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize / 2 <= OR_MAX, "outlier_removal: kernel_size=%d unsupported (odd, <= %d)", ksize, 2 * OR_MAX + 1);
+    KB_CHECK_ARG(N <= 65535 && cdiv(H, OT) <= 65535, "outlier_removal: more than 65535 samples or tile rows in one launch");
     unsigned* slot = (unsigned*)workspace;
     const long long n = (long long)N * H * W;
     max_init_kernel<<<1, 1, 0, stream>>>(slot);

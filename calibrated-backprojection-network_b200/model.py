@@ -44,7 +44,9 @@ def _conv(sources, weight, stride, slope, out=None):
 
 
 class KBNetEncoder(torch.nn.Module):
-    """reference src/networks.py:24-533 with KB layers at resolutions [0,1,2,3] (the only configuration KBNet ships)."""
+    """reference src/networks.py:24-533 with KB layers at resolutions [0,1,2,3] (the only configuration KBNet ships; it is
+    also this class's default -- the reference's own default [0,1,2] builds VGG blocks at level 3, which are not implemented
+    here and raise)."""
 
     def __init__(self,
                  input_channels_image=3,
@@ -55,7 +57,7 @@ class KBNetEncoder(torch.nn.Module):
                  n_convolutions_image=[1, 1, 1, 1, 1],
                  n_convolutions_depth=[1, 1, 1, 1, 1],
                  n_convolutions_fused=[1, 1, 1, 1, 1],
-                 resolutions_backprojection=[0, 1, 2],
+                 resolutions_backprojection=[0, 1, 2, 3],
                  weight_initializer='kaiming_uniform',
                  activation_func='leaky_relu'):
         super().__init__()
@@ -148,9 +150,9 @@ class MultiScaleDecoder(torch.nn.Module):
     """reference src/networks.py:1605-1989 for the KBNet configuration: n_resolution=1, deconv_type='up',
     output_func='linear', 5 decoder blocks."""
 
-    def __init__(self, input_channels=256, output_channels=1, n_resolution=4, n_filters=[256, 128, 64, 32, 16],
+    def __init__(self, input_channels=256, output_channels=1, n_resolution=1, n_filters=[256, 128, 64, 32, 16],
                  n_skips=[256, 128, 64, 32, 0], weight_initializer='kaiming_uniform', activation_func='leaky_relu',
-                 output_func='linear', use_batch_norm=False, use_instance_norm=False, deconv_type='transpose'):
+                 output_func='linear', use_batch_norm=False, use_instance_norm=False, deconv_type='up'):
         super().__init__()
         if n_resolution != 1 or deconv_type != 'up' or output_func != 'linear' or use_batch_norm or use_instance_norm \
                 or len(n_filters) != 5:

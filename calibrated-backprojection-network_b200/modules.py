@@ -145,10 +145,14 @@ def get_precision():
 
 
 def packed_weight(weight, src_channels):
-    """Device buffer with `weight` ([F, sum(src_channels), k, k]) re-laid for the tensor-core engine; None in fp32 mode.
+    """Device buffer with `weight` ([F, sum(src_channels), k, k]) re-laid for the tensor-core engine; None in fp32 mode or
+    when the layer is outside the engine's envelope (the exact-fp32 kernel then takes it).
     The buffer is cached ON the weight tensor object (so it dies with it -- a cache keyed on data_ptr alone would be fooled
     by the allocator handing a freed weight's address to another layer) and is re-packed when the version counter or the
-    storage changes (in-place updates, load_state_dict, .to())."""
+    storage changes: load_state_dict, optimizer steps, ``p.copy_()``, ``.to()``.  Writes THROUGH ``p.data`` (``p.data.mul_()``,
+    ``p.data.copy_()``) do not bump the version counter: call ``invalidate_packs(module)`` after such surgery.
+    Under torch.nn.DataParallel the replicas are fresh tensors every forward, so the pack is rebuilt per forward there
+    (DataParallel re-broadcasts all weights each forward anyway, src/kbnet_model.py:408-415)."""
     if _PRECISION != 'bf16x3':
         return None
     key = (weight.data_ptr(), weight._version, tuple(int(c) for c in src_channels), tuple(weight.shape))
@@ -162,7 +166,7 @@ def packed_weight(weight, src_channels):
     arr = (ctypes.c_int * len(src_channels))(*[int(c) for c in src_channels])
     nbytes = lib.kbnet_conv_wpack_bytes(arr, len(src_channels), f, k)
     if nbytes == 0:
-        raise RuntimeError('kbnet_b200: convolution with %d input channels / %d filters is outside the tensor-core engine' % (ctot, f))
+        return None
     buf = torch.empty((nbytes,), dtype=torch.uint8, device=wc.device)
     with torch.cuda.device(wc.device):
         rc = lib.kbnet_conv_pack_weights(wc.data_ptr(), arr, len(src_channels), f, k, buf.data_ptr(), _stream(wc.device))
@@ -172,6 +176,16 @@ def packed_weight(weight, src_channels):
     except Exception:
         pass
     return buf
+
+
+def invalidate_packs(module):
+    """Drop every cached packed-weight image under `module` (needed only after writes through ``param.data``, which do
+    not bump the tensor version the caches are keyed on)."""
+    for m in module.modules():
+        m.__dict__.pop('_kbnet_s2d_pack', None)
+    for p in module.parameters():
+        for k in ('_kbnet_pack', '_kbnet_up2x'):
+            p.__dict__.pop(k, None)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -324,7 +338,11 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
         o_i, o_d, o_f = _out(out_image, f_i), _out(out_depth, f_d), _out(out_fused, f_f)
         lib = _lib.load()
         ws_bytes = lib.kbnet_kb_workspace_bytes(n, c_i, c_d, c_f, h, w, f_i, f_d, f_f)
-        ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=dev)
+        # scratch for the un-fused path (z at even pixels); kept on the module and re-used: no allocation per call
+        ws = self.__dict__.get('_kbnet_ws')
+        if ws is None or ws.device != dev or ws.numel() < max(int(ws_bytes), 256):
+            ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=dev)
+            self.__dict__['_kbnet_ws'] = ws
         wi, wd = _w(self.conv_image.weight, dev), _w(self.conv_depth.weight, dev)
         wp, wf = _w(self.proj_depth.weight, dev), _w(self.conv_fused.weight, dev)
         sn = lambda t: t.stride(0) if n > 1 else t.shape[1] * ho * wo

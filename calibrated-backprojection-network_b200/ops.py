@@ -36,6 +36,10 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
         raise RuntimeError('kbnet_b200: conv2d_fused needs a size for upsample-only inputs')
     dev = parsed[0][0].device
     n = parsed[0][0].shape[0]
+    for t, _, _ in parsed[1:]:
+        if t.shape[0] != n or t.device != dev:
+            raise RuntimeError('kbnet_b200: conv2d_fused sources disagree on batch size / device: %s on %s vs N=%d on %s'
+                               % (tuple(t.shape), t.device, n, dev))
     w = _w(weight, dev)
     f, ctot, k, _ = w.shape
     if sum(t.shape[1] for t, _, _ in parsed) != ctot:
@@ -45,7 +49,7 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
     ho, wo = (h_in + 2 * pad - k) // stride + 1, (w_in + 2 * pad - k) // stride + 1
     if out is None:
         out = torch.empty((n, f, ho, wo), dtype=torch.float32, device=dev)
-    elif tuple(out.shape) != (n, f, ho, wo) or out.stride()[1:] != (ho * wo, wo, 1) or out.dtype != torch.float32:
+    elif tuple(out.shape) != (n, f, ho, wo) or out.stride()[1:] != (ho * wo, wo, 1) or out.dtype != torch.float32 or out.device != dev:
         raise RuntimeError('kbnet_b200: bad preallocated conv output')
     osn = out.stride(0) if n > 1 else f * ho * wo
     from .modules import get_precision
@@ -112,6 +116,9 @@ def upconv2x(x, weight, slope=0.2, out=None):
     _w(weight, dev)
     if out is None:
         out = torch.empty((n, f, 2 * hs, 2 * ws), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, f, 2 * hs, 2 * ws) or out.stride()[1:] != (4 * hs * ws, 2 * ws, 1) or out.dtype != torch.float32 \
+            or out.device != dev:
+        raise RuntimeError('kbnet_b200: bad preallocated upconv2x output')
     packs = _upconv_packs(weight)
     arr = (ctypes.c_void_p * 4)(*[pk.data_ptr() for pk in packs])
     osn = out.stride(0) if n > 1 else f * 4 * hs * ws

@@ -13,8 +13,12 @@
  *   - the device is the CURRENT device of the calling thread (caller does cudaSetDevice / torch.cuda.device);
  *   - return value: 0 on success, non-zero on failure (cudaError_t value, or KBNET_E_* below);
  *     kbnet_last_error() returns a thread-local message for the last failure on this thread;
- *   - no global mutable state: safe to call concurrently from several host threads / streams
- *     (torch.nn.DataParallel replicas call forward from one thread per device).
+ *   - thread safety: every entry point may be called concurrently from several host threads / streams
+ *     (torch.nn.DataParallel replicas call forward from one thread per device).  Process-wide state is limited to
+ *     (i) two relaxed launch counters (statistics), (ii) a mutex-guarded memo of tile plans keyed by layer shape
+ *     (a pure function of the shape unless autotuning is on), and (iii) the kbnet_set_autotune switch, which is
+ *     process-global by design: when on, the FIRST call for a new layer shape times candidate tilings and
+ *     synchronises the stream once (never inside a CUDA-graph capture: settle shapes with a warm-up call first).
  */
 #ifndef KBNET_B200_H_
 #define KBNET_B200_H_
