@@ -50,7 +50,8 @@ constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+16  (18 x 17 = 
 constexpr int LV = 9;            // pass-1 rows per work item (two items per tile column)
 constexpr int PW = TW + 4;       // conv-input cols   x0-2 .. x0+65  (17 strips of 4)
 constexpr int XP = PW + 4;       // smem pitch of the raw-channel tile: TMA boxes start at x0-4 (16-byte aligned coordinate)
-constexpr int XCP = PW + 1;      // pitch of the packed raw-channel planes: entry PW of every row is zero (unused mma k-slots read it)
+constexpr int XCP = PW + 2;      // pitch (32-bit words) of a packed raw-channel plane row: words PW, PW + 1 are zero (unused mma k-slots read them)
+constexpr int QROW = PW;         // Q plane row: 34 even-column entries, then 34 odd-column entries (16 bytes each)
 constexpr int NT = 320;
 constexpr int CONV_WARPS = 8;    // phase D: 4 column blocks x 2 row groups
 constexpr int LH = 4;            // pass-2 strip width
@@ -100,8 +101,8 @@ __host__ __device__ inline Layout make_layout(int R, int n_pool, int n_conv) {
     int o = 16;  // [0,8): mbarrier
     L.w1 = o; o += w1_bytes(n_pool, n_conv);
     L.wB = o; o += WB_BYTES;
-    L.xch = o; o += PH * XCP * 8;
-    L.xcl = o; o += PH * XCP * 8;
+    L.xch = o; o += PH * XCP * 4;
+    L.xcl = o; o += PH * XCP * 4;
     o = (o + 15) & ~15;
     L.v = o; o += n_pool * PH * ZW * 4;
     o = (o + 127) & ~127;
@@ -455,8 +456,11 @@ __device__ __forceinline__ void pass2(const FastParams& p, const float* __restri
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) { hi[jp] = inb ? hi[jp] : 0u; lo[jp] = inb ? lo[jp] : 0u; }
         }
-        s_qhi[pr * PW + c0 + i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        s_qlo[pr * PW + c0 + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        // column c -> plane (c & 1), entry (c >> 1): the conv's mma rows are the even pixels, then the odd pixels of a block
+        // (adjacent pixels per lane -> 8-byte output stores), and a strip's four stores hit 2 banks groups instead of 1
+        const int e = pr * QROW + (i & 1) * (QROW / 2) + ((c0 + i) >> 1);
+        s_qhi[e] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        s_qlo[e] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -471,8 +475,8 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     const Layout L = make_layout(R, np, n_conv);
     float* s_w1 = reinterpret_cast<float*>(smem + L.w1);
     uint2* s_wB = reinterpret_cast<uint2*>(smem + L.wB);
-    uint32_t* s_xch = reinterpret_cast<uint32_t*>(smem + L.xch);   // [row][XCP] pairs (hi[c], hi[c + 8])
-    uint32_t* s_xcl = reinterpret_cast<uint32_t*>(smem + L.xcl);   // [row][XCP] pairs (lo[c], lo[c + 8])
+    uint32_t* s_xch = reinterpret_cast<uint32_t*>(smem + L.xch);   // [row][XCP] packed bf16 hi words of the raw channels
+    uint32_t* s_xcl = reinterpret_cast<uint32_t*>(smem + L.xcl);   // ... and the lo words
     float* s_V = reinterpret_cast<float*>(smem + L.v);
     float* s_z = reinterpret_cast<float*>(smem + L.z);
     float* s_x1 = reinterpret_cast<float*>(smem + L.x1);
@@ -539,9 +543,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         } else {
             // raw channels of the 3x3 conv input as packed bf16 words (two k-slots each):
             //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
-            // stored as 8-byte entries (word[c], word[c + 8]) -- the two pixel halves of an mma A fragment -- so that one
-            // LDS.64 fills two consecutive fragment registers.  Entry PW of every row is zero: k-slots that carry no raw
-            // channel read it.
+            // words PW, PW + 1 of every row are zero: k-slots that carry no raw channel read them
             constexpr int STEP = NT - T_P1;
             int idx = tid - T_P1, pr = idx / XCP, c = idx - pr * XCP;
             for (; idx < PH * XCP; idx += STEP, c += STEP % XCP, pr += STEP / XCP) {
@@ -552,10 +554,8 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
                     const float bb = C_in > 1 ? s_x1[pr * XP + c + 2] : s_z[(pr + R) * ZP + c + R + 3];
                     split_rn(a, bb, hi, lo);
                 }
-                s_xch[2 * idx] = hi;
-                s_xcl[2 * idx] = lo;
-                if (c >= 8 && c < PW) { s_xch[2 * (idx - 8) + 1] = hi; s_xcl[2 * (idx - 8) + 1] = lo; }
-                if (c >= PW - 8) { s_xch[2 * idx + 1] = 0u; s_xcl[2 * idx + 1] = 0u; }
+                s_xch[idx] = hi;
+                s_xcl[idx] = lo;
             }
         }
     }
@@ -584,68 +584,83 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             bf[ks][0] = s_wB[(ks * 2 + 0) * 32 + lane];
             bf[ks][1] = s_wB[(ks * 2 + 1) * 32 + lane];
         }
-        float acc[LR][4];
-#pragma unroll
-        for (int i = 0; i < LR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        // ldmatrix row addresses: matrix m = lane / 8 -> pixel half (m & 1), chunk (m >> 1); row = lane & 7
-        const int mrow = ((lane >> 3) & 1) * 8 + (lane & 7);
-        const int col_s0 = 16 * cb + mrow + 1 + (lane >> 4);  // k-step half 0: dx = 0 (chunk A), dx = 1 (chunk B)
-        const int col_s1 = 16 * cb + mrow + 1 + 2;            // k-step half 1, chunk A: dx = 2
-        // raw-channel fragment: lane t holds slots (2t, 2t+1); a lane whose slots carry nothing reads the zero entry of the row
+        // mma row r <-> block pixel m = 2r (r < 8) or 2(r - 8) + 1: the fragment registers of one lane hold ADJACENT pixels, so the
+        // raw-channel words are adjacent and the output stores are 8-byte accesses.  Q column of (pixel m, tap dx) =
+        // 16 cb + m + 1 + dx; columns live in an even plane and an odd plane, so the 8 rows of every ldmatrix matrix are
+        // consecutive 16-byte entries.  ldmatrix row addresses: matrix mi = lane / 8 -> row half (mi & 1), k chunk (mi >> 1).
+        const int mi = lane >> 3, mr = lane & 7;
+        const int c_s0 = 16 * cb + 2 * mr + 1 + (mi & 1) + (mi >> 1);   // k-step half 0: chunk 0 = dx 0, chunk 1 = dx 1
+        const int c_s1 = 16 * cb + 2 * mr + 1 + (mi & 1) + 2;           // k-step half 1, chunk 0: dx = 2 (x2: lanes 0-15)
+        const uint32_t e_s0 = (uint32_t)((c_s0 & 1) * (QROW / 2) + (c_s0 >> 1) + LR * rg * QROW) * 16u;
+        const uint32_t e_s1 = (uint32_t)((c_s1 & 1) * (QROW / 2) + (c_s1 >> 1) + LR * rg * QROW) * 16u;
+        // raw-channel fragment: lane t holds k-slots (2t, 2t+1) of pixels 2g and 2g + 1 (adjacent words); a lane whose slots
+        // carry nothing reads the zero words at the end of the row
         int col_x;
         uint32_t xmask = 0xFFFFFFFFu;
-        if (C_in > 1) { col_x = t < 3 ? 16 * cb + g + 1 + t : PW; }
-        else          { col_x = t < 2 ? 16 * cb + g + 1 + 2 * t : PW; xmask = t == 1 ? 0x0000FFFFu : 0xFFFFFFFFu; }
-        const uint32_t q_row0 = (uint32_t)(LR * rg * PW) * 16u;
-        const uint32_t a_s0h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s0 * 16u, a_s0l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s0 * 16u;
-        const uint32_t a_s1h = smem_u32(s_qhi) + q_row0 + (uint32_t)col_s1 * 16u, a_s1l = smem_u32(s_qlo) + q_row0 + (uint32_t)col_s1 * 16u;
-        const uint2* xrow_h = reinterpret_cast<const uint2*>(s_xch) + LR * rg * XCP + col_x;
-        const uint2* xrow_l = reinterpret_cast<const uint2*>(s_xcl) + LR * rg * XCP + col_x;
+        if (C_in > 1) { col_x = t < 3 ? 16 * cb + 2 * g + 1 + t : PW; }
+        else          { col_x = t < 2 ? 16 * cb + 2 * g + 1 + 2 * t : PW; xmask = t == 1 ? 0x0000FFFFu : 0xFFFFFFFFu; }
+        const uint32_t qh = smem_u32(s_qhi), ql = smem_u32(s_qlo);
+        const uint32_t* xrow_h = s_xch + LR * rg * XCP + col_x;
+        const uint32_t* xrow_l = s_xcl + LR * rg * XCP + col_x;
+        // epilogue addressing: c0,c1 = (pixel 2g, filters 2t, 2t+1), c2,c3 = (pixel 2g + 1, same filters)
+        const int gxa = x0 + 16 * cb + 2 * g;
+        float* d0 = p.out + ((size_t)n * NF + 2 * t) * plane + (size_t)(y0 + LR * rg) * W + gxa;
+        const bool full = y0 + TH <= H && x0 + TW <= W && (W & 1) == 0 && ((uintptr_t)p.out & 7) == 0;   // every tile of the shipped shapes
+        const bool in_a = gxa < W, in_b = gxa + 1 < W;
+        float* r0 = d0;                                    // output row pointers (filters 2t and 2t + 1), advanced row by row
+        float* r1 = d0 + plane;
+        // Only three output rows are open at any time (row li takes tap rows li .. li + 2); the issue order walks them
+        // round-robin so that consecutive HMMAs never touch the same accumulator (a dependent HMMA waits for its predecessor).
+        float acc[3][4];
 #pragma unroll
         for (int qr = 0; qr < LR + 2; ++qr) {
             uint32_t a0h[4], a0l[4], a1h[4], a1l[4];
-            ldsm_x4(a_s0h + (uint32_t)(qr * PW * 16), a0h);
-            ldsm_x4(a_s0l + (uint32_t)(qr * PW * 16), a0l);
-            ldsm_x2(a_s1h + (uint32_t)(qr * PW * 16), a1h[0], a1h[1]);
-            ldsm_x2(a_s1l + (uint32_t)(qr * PW * 16), a1l[0], a1l[1]);
-            const uint2 xh = xrow_h[qr * XCP], xl = xrow_l[qr * XCP];
-            if (C_in > 1) { a1h[2] = xh.x; a1h[3] = xh.y; a1l[2] = xl.x; a1l[3] = xl.y; }
-            else          { a1h[2] = xh.x & xmask; a1h[3] = xh.y & xmask; a1l[2] = xl.x & xmask; a1l[3] = xl.y & xmask; }
+            ldsm_x4(qh + e_s0 + (uint32_t)(qr * QROW * 16), a0h);
+            ldsm_x4(ql + e_s0 + (uint32_t)(qr * QROW * 16), a0l);
+            ldsm_x2(qh + e_s1 + (uint32_t)(qr * QROW * 16), a1h[0], a1h[1]);
+            ldsm_x2(ql + e_s1 + (uint32_t)(qr * QROW * 16), a1l[0], a1l[1]);
+            a1h[2] = xrow_h[qr * XCP]; a1h[3] = xrow_h[qr * XCP + 1];
+            a1l[2] = xrow_l[qr * XCP]; a1l[3] = xrow_l[qr * XCP + 1];
+            if (C_in == 1) { a1h[2] &= xmask; a1h[3] &= xmask; a1l[2] &= xmask; a1l[3] &= xmask; }
+            if (qr < LR) {                                 // output row qr opens with tap row 0
+                float (&m)[4] = acc[qr % 3];
+                m[0] = m[1] = m[2] = m[3] = 0.f;
+            }
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const int li = qr - dy;
-                if (li >= 0 && li < LR) {
-                    hmma(acc[li], a0h, bf[2 * dy][0].x, bf[2 * dy][0].y);
-                    hmma(acc[li], a0l, bf[2 * dy][0].x, bf[2 * dy][0].y);
-                    hmma(acc[li], a0h, bf[2 * dy][1].x, bf[2 * dy][1].y);
-                    hmma(acc[li], a1h, bf[2 * dy + 1][0].x, bf[2 * dy + 1][0].y);
-                    hmma(acc[li], a1l, bf[2 * dy + 1][0].x, bf[2 * dy + 1][0].y);
-                    hmma(acc[li], a1h, bf[2 * dy + 1][1].x, bf[2 * dy + 1][1].y);
+            for (int term = 0; term < 6; ++term) {         // (A fragment, B fragment) pairs of one tap row
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int li = qr - dy;
+                    if (li >= 0 && li < LR) {
+                        const int ks = 2 * dy + (term >= 3 ? 1 : 0);
+                        const uint2 bh = bf[ks][0], bl = bf[ks][1];
+                        const int tt = term % 3;           // 0: a_hi b_hi   1: a_lo b_hi   2: a_hi b_lo
+                        if (term < 3) {
+                            if (tt == 0)      hmma(acc[li % 3], a0h, bh.x, bh.y);
+                            else if (tt == 1) hmma(acc[li % 3], a0l, bh.x, bh.y);
+                            else              hmma(acc[li % 3], a0h, bl.x, bl.y);
+                        } else {
+                            if (tt == 0)      hmma(acc[li % 3], a1h, bh.x, bh.y);
+                            else if (tt == 1) hmma(acc[li % 3], a1l, bh.x, bh.y);
+                            else              hmma(acc[li % 3], a1h, bl.x, bl.y);
+                        }
+                    }
                 }
             }
-        }
-        // epilogue: c0,c1 = (pixel g, filters 2t, 2t+1), c2,c3 = (pixel g + 8, same filters)
-        const int gxa = x0 + 16 * cb + g;
-        float* d0 = p.out + ((size_t)n * NF + 2 * t) * plane + (size_t)(y0 + LR * rg) * W + gxa;
-        float* d1 = d0 + plane;
-        if (y0 + TH <= H && x0 + TW <= W) {           // full tile (every tile of the shipped shapes): no bounds checks
-#pragma unroll
-            for (int li = 0; li < LR; ++li) {
-                float v0, v1, v2, v3;
-                unpack2(leaky01x2(pack2(acc[li][0], acc[li][1]), slope), v0, v1);
-                unpack2(leaky01x2(pack2(acc[li][2], acc[li][3]), slope), v2, v3);
-                d0[0] = v0; d1[0] = v1; d0[8] = v2; d1[8] = v3;
-                d0 += W; d1 += W;
-            }
-        } else {
-            const bool in_a = gxa < W, in_b = gxa + 8 < W;
-#pragma unroll
-            for (int li = 0; li < LR; ++li) {
-                if (y0 + LR * rg + li < H) {
-                    if (in_a) { d0[0] = leaky01(acc[li][0], slope); d1[0] = leaky01(acc[li][1], slope); }
-                    if (in_b) { d0[8] = leaky01(acc[li][2], slope); d1[8] = leaky01(acc[li][3], slope); }
+            if (qr >= 2) {                                 // output row qr - 2 is complete: LeakyReLU, 8-byte stores
+                const int li = qr - 2;
+                const float (&a)[4] = acc[li % 3];
+                if (full) {
+                    float v0, v1, v2, v3;
+                    unpack2(leaky01x2(pack2(a[0], a[1]), slope), v0, v1);
+                    unpack2(leaky01x2(pack2(a[2], a[3]), slope), v2, v3);
+                    *reinterpret_cast<float2*>(r0) = make_float2(v0, v2);
+                    *reinterpret_cast<float2*>(r1) = make_float2(v1, v3);
+                } else if (y0 + LR * rg + li < H) {
+                    if (in_a) { r0[0] = leaky01(a[0], slope); r1[0] = leaky01(a[1], slope); }
+                    if (in_b) { r0[1] = leaky01(a[2], slope); r1[1] = leaky01(a[3], slope); }
                 }
-                d0 += W; d1 += W;
+                r0 += W; r1 += W;
             }
         }
     }
