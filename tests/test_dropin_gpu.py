@@ -37,6 +37,12 @@ def _inputs(n, h, w, seed, skew=False):
 
 def _pair(cfg, device):
     """(unpatched reference model on the CPU, patched reference model on `device`) with identical weights"""
+    # The reference calls torch.inverse inside the DataParallel replicas (src/networks.py:328), i.e. from one thread per GPU;
+    # torch's lazy linalg initialisation is not thread-safe on first use ("lazy wrapper should be called at most once"), so
+    # initialise it on the main thread for every visible device first.  (Stock-PyTorch behaviour, nothing of this library.)
+    for d in range(torch.cuda.device_count()):
+        torch.inverse(torch.eye(3, device='cuda:%d' % d).unsqueeze(0))
+    torch.cuda.synchronize()
     networks, net_utils, kbnet_model, _ = MODS
     ref = refload.build_reference_model(cfg, torch.device('cpu'), cfg['f_img'], cfg['f_dep'], cfg['f_dec'], seed=3)
     orig = kbnet_b200.install(networks, net_utils)
