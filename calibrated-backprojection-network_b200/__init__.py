@@ -4,13 +4,13 @@ layers behind the reference's own nn.Module interface, plus the encoder/decoder 
 Importable as ``kbnet_b200`` (see kbnet_b200.py at the repository root; this directory keeps the name the build
 contract asks for).  The compute lives in libkbnet_b200.so (csrc/, C ABI in include/kbnet_b200.h).
 """
-from . import _lib, build as _build, dist, ops
+from . import _lib, build as _build, dist, io, ops
 from .modules import (CalibratedBackprojectionBlock, OutlierRemoval, SparseToDensePool, install, invalidate_packs, set_precision,
                       get_precision)
 from .model import GraphRunner, KBNetEncoder, KBNetModel, MultiScaleDecoder
 
 __all__ = ['SparseToDensePool', 'CalibratedBackprojectionBlock', 'OutlierRemoval', 'KBNetEncoder', 'MultiScaleDecoder', 'KBNetModel',
-           'install', 'invalidate_packs', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'build_library', 'library_path']
+           'install', 'invalidate_packs', 'set_precision', 'get_precision', 'set_autotune', 'ops', 'dist', 'io', 'build_library', 'library_path']
 
 
 def build_library(force=False, verbose=False):

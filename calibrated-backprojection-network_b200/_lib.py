@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
 
-EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_set_autotune', 'kbnet_upconv2x_supported', 'kbnet_upconv2x_prepare_weights', 'kbnet_upconv2x_forward', 'kbnet_outlier_removal_forward', 'kbnet_conv3x3_depth_head_forward', 'kbnet_conv3x3_small_supported', 'kbnet_conv3x3_small_forward', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
+EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_set_autotune', 'kbnet_upconv2x_supported', 'kbnet_upconv2x_prepare_weights', 'kbnet_upconv2x_forward', 'kbnet_outlier_removal_forward', 'kbnet_conv3x3_depth_head_forward', 'kbnet_conv3x3_small_supported', 'kbnet_conv3x3_small_forward', 'kbnet_depth_u16_decode', 'kbnet_depth_u16_encode', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
            'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights', 'kbnet_intrinsics_inverse')
 
 
@@ -69,6 +69,10 @@ def load():
     lib.kbnet_conv3x3_small_supported.argtypes = [i, i, i, i]
     lib.kbnet_conv3x3_small_forward.restype = i
     lib.kbnet_conv3x3_small_forward.argtypes = [vp, ll, i, i, i, i, vp, i, i, f, vp, ll, vp]
+    lib.kbnet_depth_u16_decode.restype = i
+    lib.kbnet_depth_u16_decode.argtypes = [vp, ll, vp, vp, vp]
+    lib.kbnet_depth_u16_encode.restype = i
+    lib.kbnet_depth_u16_encode.argtypes = [vp, ll, vp, vp]
     lib.kbnet_depth_head_forward.restype = i
     lib.kbnet_depth_head_forward.argtypes = [vp, ll, c.c_double, c.c_double, vp, vp]
     _lib = lib

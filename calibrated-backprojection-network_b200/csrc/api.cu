@@ -249,6 +249,19 @@ int kbnet_outlier_removal_forward(const float* sparse_depth, const float* validi
                                   (cudaStream_t)stream);
 }
 
+/* element-wise half of the reference's 16-bit-PNG depth I/O (csrc/depth_io.cu) */
+int kbnet_depth_u16_decode(const uint16_t* z16, long long n_elem, float* depth, float* validity, void* stream) {
+    KB_CHECK_ARG(n_elem >= 0 && (n_elem == 0 || (z16 && depth)), "depth_u16_decode: bad argument");
+    KB_CHECK_ARG(n_elem < (1ll << 39), "depth_u16_decode: too many elements in one launch");
+    return depth_u16_decode_launch(z16, n_elem, depth, validity, (cudaStream_t)stream);
+}
+
+int kbnet_depth_u16_encode(const float* depth, long long n_elem, uint32_t* out, void* stream) {
+    KB_CHECK_ARG(n_elem >= 0 && (n_elem == 0 || (depth && out)), "depth_u16_encode: bad argument");
+    KB_CHECK_ARG(n_elem < (1ll << 39), "depth_u16_encode: too many elements in one launch");
+    return depth_u16_encode_launch(depth, n_elem, out, (cudaStream_t)stream);
+}
+
 int kbnet_depth_head_forward(const float* x, long long n_elem, double min_depth, double max_depth, float* y, void* stream) {
     KB_CHECK_ARG(x && y && n_elem >= 0, "depth_head: bad argument");
     return depth_head_launch(x, n_elem, min_depth, max_depth, y, (cudaStream_t)stream);

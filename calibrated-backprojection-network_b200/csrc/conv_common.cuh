@@ -100,6 +100,8 @@ int conv_small_launch(const float* x, long long x_stride_n, int N, int C, int H,
 bool conv_mma_supported(int C, int F, int ksize, int stride);
 int conv_mma_launch(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act, float slope, float* out,
                     long long out_stride_n, cudaStream_t stream);
+int depth_u16_decode_launch(const uint16_t* z16, long long n, float* depth, float* validity, cudaStream_t stream);
+int depth_u16_encode_launch(const float* depth, long long n, uint32_t* out, cudaStream_t stream);
 int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);
 int s2d_forward(const float* x, int N, int C_in, int H, int W, const int* min_sizes, int n_min, const int* max_sizes,
                 int n_max, const float* const* w_1x1, int n_conv, int n_filter, const float* w_3x3, const void* wpack, float neg_slope,

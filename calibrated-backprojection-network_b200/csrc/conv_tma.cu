@@ -46,10 +46,10 @@ constexpr int V2_MAX_STAGES = 72;
 constexpr int V2_MAX_CONVS = 4;
 constexpr int V2_MAX_USES = 4;
 constexpr int V2_MAX_MAPS = 4;
-// converter warps per geometry (a multiple of 4: the epilogue warps sit at conv_warps + 4 .. + 7 and address TMEM lane quarter
-// warp % 4).  12 warps were measured for the stride-2 programs (they fit: ~80 registers) and changed nothing -- the KB block is
-// bound by the latency chain raw TMA -> convert -> MMA -> commit of its two operand stages, not by converter throughput.
-__host__ __device__ constexpr int conv_warps(int geo) { return geo >= 0 ? 8 : 8; }
+// converter warps (a multiple of 4: the epilogue warps sit at conv_warps + 4 .. + 7 and address TMEM lane quarter warp % 4).
+// 12 warps were measured for the stride-2 programs (they fit: ~80 registers) and changed nothing -- the KB block is bound by the
+// latency chain raw TMA -> convert -> MMA -> commit of its two operand stages, not by converter throughput.
+__host__ __device__ constexpr int conv_warps(int) { return 8; }
 __host__ __device__ constexpr int cta_threads(int geo) { return (conv_warps(geo) + 8) * 32; }
 constexpr int V2_MAX_RAW = 6, V2_MAX_A = 3, V2_MAX_W = 8;
 constexpr int V2_HEADER = 2048;
@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                     for (int i = 0; i < MAXI; ++i) {
                         if (GEO == G_S2K3 && i < n_it && it_e[i] < p.n_entries) {
                             const int e = it_e[i];
-                            if (false) {
-                            } else {  // G_S2K3: four parity planes
+                            {  // G_S2K3: four parity planes
                                 const int y0 = 2 * (tc.oy0 - 1 + it_ei[i]), x0 = 2 * (tc.ox0 - 1 + it_ej[i]);
                                 if (kind == CK_TMA) {
                                     const float* r = raw + ro0[i];

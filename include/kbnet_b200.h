@@ -181,6 +181,14 @@ int kbnet_conv3x3_small_supported(int C, int F, int ksize, int stride);
 int kbnet_conv3x3_small_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
                                 float neg_slope, float* y, long long y_stride_n, void* stream);
 
+/* Element-wise half of the reference's on-disk depth format -- a 16-bit PNG holding depth * 256 (src/data_utils.py:88-167;
+ * the PNG container itself is host work, kbnet_b200/io.py).
+ * decode: depth = u16 / 256, values <= 0 -> 0 (load_depth, :137-141); validity (may be NULL) = 1 where depth > 0 else depth
+ *         (load_depth_with_validity_map, :100-107).  z16 is a DEVICE pointer to n_elem uint16 values.
+ * encode: out = uint32(depth * 256), C truncation (save_depth, :165).  Both bit-exact against numpy. */
+int kbnet_depth_u16_decode(const uint16_t* z16, long long n_elem, float* depth, float* validity, void* stream);
+int kbnet_depth_u16_encode(const float* depth, long long n_elem, uint32_t* out, void* stream);
+
 /* OutlierRemoval.remove_outliers (reference src/net_utils.py:1761-1806): drop sparse points that are more than `threshold`
  * behind the nearest point of their kernel_size x kernel_size neighbourhood.  sparse_depth / validity_map / outputs are
  * [N,1,H,W]; validity_map may be NULL, then it is derived as in src/kbnet.py:899-902 (depth > 0 ? 1 : depth).  The global
