@@ -466,14 +466,20 @@ def main():
 
     # ---- N ranks == 1 rank, on hardware: SHA-256 of every shard's output.  Rank r reports shard r; a single-GPU run also
     # computes shards 1..7 (outside the timed regions) so that its list can be compared with an 8-GPU run's list.
-    shard_shas = [shard_sha]
+    # The timed runs use MEASURED tile plans (autotune), which may differ from process to process (e.g. the two-MMA "dual"
+    # form vs three MMAs: same mathematics, different fp32 rounding), so the cross-run hashes are taken from one extra
+    # forward with the deterministic cost-model plans (autotune off; plans are memoised separately per mode).
+    kbnet_b200.set_autotune(False)
+    det_sha = sha256_of(model.forward(*resident))
+    shard_shas = [det_sha]
     if world > 1:
         gathered = [None] * world
-        dist.all_gather_object(gathered, shard_sha)
+        dist.all_gather_object(gathered, det_sha)
         shard_shas = gathered
     elif not args.no_shard_check:
         for r in range(1, 8):
             shard_shas.append(sha256_of(model.forward(*[t.to(dev) for t in synth_inputs(cfg, nb, 1 + r)])))
+    kbnet_b200.set_autotune(not args.no_autotune)
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, s2d_ms, kb_ms], device=dev, dtype=torch.float64)
@@ -514,6 +520,7 @@ def main():
         'gpu_launches_per_step': int(launches_per_step),
         'clocks': clocks,
         'shard_output_sha256_16': shard_shas,
+        'shard_output_note': 'SHA-256 (16 hex) of the output of shard r = synth_inputs(seed 1 + r), forward with the deterministic (cost-model) tile plans; rank r of an N-rank run reports shard r, a 1-rank run reports shards 0..7',
         'roofline': {'kernel': 's2d kernel (SparseToDensePool, one launch)', 'bound': 'hbm', 'achieved': s2d_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': s2d_gbs / hbm_peak, 'traffic': ncu_traffic('s2d_fused_kernel') if is_kitti8 else None, 'peak_kind': peak_kind,
                      'algorithmic_bytes_per_launch': s2d_bytes, 'ms_per_launch': s2d_ms,
