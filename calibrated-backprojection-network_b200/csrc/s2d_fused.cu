@@ -50,7 +50,7 @@ constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+16  (18 x 17 = 
 constexpr int LV = 9;            // pass-1 rows per work item (two items per tile column)
 constexpr int PW = TW + 4;       // conv-input cols   x0-2 .. x0+65  (17 strips of 4)
 constexpr int XP = PW + 4;       // smem pitch of the raw-channel tile: TMA boxes start at x0-4 (16-byte aligned coordinate)
-constexpr int XCP = PW + 2;      // pitch (32-bit words) of a packed raw-channel plane row: words PW, PW + 1 are zero (unused mma k-slots read them)
+constexpr int XCP = PW + 4;      // pitch (32-bit words) of a packed raw-channel plane row: words PW .. PW + 3 are zero (unused mma k-slots read them)
 constexpr int QROW = PW;         // Q plane row: 34 even-column entries, then 34 odd-column entries (16 bytes each)
 constexpr int NT = 320;
 constexpr int CONV_WARPS = 8;    // phase D: 4 column blocks x 2 row groups
@@ -101,6 +101,7 @@ __host__ __device__ inline Layout make_layout(int R, int n_pool, int n_conv) {
     int o = 16;  // [0,8): mbarrier
     L.w1 = o; o += w1_bytes(n_pool, n_conv);
     L.wB = o; o += WB_BYTES;
+    o = (o + 15) & ~15;
     L.xch = o; o += PH * XCP * 4;
     L.xcl = o; o += PH * XCP * 4;
     o = (o + 15) & ~15;
@@ -544,18 +545,35 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             // raw channels of the 3x3 conv input as packed bf16 words (two k-slots each):
             //   C_in == 2: (x0, x1) of this pixel;   C_in == 1: x0 of this pixel and of the next one to the right
             // words PW, PW + 1 of every row are zero: k-slots that carry no raw channel read them
-            constexpr int STEP = NT - T_P1;
-            int idx = tid - T_P1, pr = idx / XCP, c = idx - pr * XCP;
-            for (; idx < PH * XCP; idx += STEP, c += STEP % XCP, pr += STEP / XCP) {
-                if (c >= XCP) { c -= XCP; ++pr; }
-                uint32_t hi = 0u, lo = 0u;
-                if (c < PW) {
-                    const float a = s_z[(pr + R) * ZP + c + R + 2];
-                    const float bb = C_in > 1 ? s_x1[pr * XP + c + 2] : s_z[(pr + R) * ZP + c + R + 3];
-                    split_rn(a, bb, hi, lo);
+            // four columns per work item: 8-byte loads of the two raw rows, 16-byte stores of the hi and the lo words
+            constexpr int STEP = NT - T_P1, NG = XCP / 4;      // column groups per row
+            static_assert(XCP % 4 == 0 && (R % 2) == 0, "8-byte alignment of the raw-row loads, 16-byte alignment of the word stores");
+            int it = tid - T_P1, pr = it / NG, cg = it - pr * NG;
+            for (; it < PH * NG; it += STEP, cg += STEP % NG, pr += STEP / NG) {
+                if (cg >= NG) { cg -= NG; ++pr; }
+                const int c = 4 * cg;
+                float a[5], bb[4];
+                const float* zr = s_z + (pr + R) * ZP + c + R + 2;     // even float offset: 8-byte aligned
+                if (c + 4 <= PW) {
+                    const float2 z0 = *reinterpret_cast<const float2*>(zr), z1 = *reinterpret_cast<const float2*>(zr + 2);
+                    a[0] = z0.x; a[1] = z0.y; a[2] = z1.x; a[3] = z1.y;
+                    a[4] = C_in > 1 ? 0.f : zr[4];
+                    if (C_in > 1) {
+                        const float* xr = s_x1 + pr * XP + c + 2;
+                        const float2 x0v = *reinterpret_cast<const float2*>(xr), x1v = *reinterpret_cast<const float2*>(xr + 2);
+                        bb[0] = x0v.x; bb[1] = x0v.y; bb[2] = x1v.x; bb[3] = x1v.y;
+                    } else {
+                        bb[0] = a[1]; bb[1] = a[2]; bb[2] = a[3]; bb[3] = a[4];
+                    }
+                } else {                                               // the zero words at the end of the row
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a[e] = bb[e] = 0.f;
                 }
-                s_xch[idx] = hi;
-                s_xcl[idx] = lo;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_rn(a[e], bb[e], hi[e], lo[e]);
+                *reinterpret_cast<uint4*>(s_xch + pr * XCP + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(s_xcl + pr * XCP + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
     }
