@@ -47,7 +47,9 @@ typedef unsigned long long u64;
 constexpr int NF = 8;            // n_filter of the fast path
 constexpr int TH = 16, TW = 64;  // output tile (352 = 22 x 16, 480 = 30 x 16, 1216 = 19 x 64, 640 = 10 x 64: no partial tiles)
 constexpr int PH = TH + 2;       // conv-input rows   y0-1 .. y0+16  (18 x 17 = 306 strips: one round of 320 threads)
-constexpr int LV = 9;            // pass-1 rows per work item (two items per tile column)
+// pass-1 rows per work item: three 6-row items per tile column leave two warps for the raw-channel split at R <= 8 (252 items);
+// at R = 16 (200 columns) two 9-row items per column do
+__host__ __device__ constexpr int lv_of(int R) { return R <= 8 ? 6 : 9; }
 constexpr int PW = TW + 4;       // conv-input cols   x0-2 .. x0+65  (17 strips of 4)
 constexpr int XP = PW + 4;       // smem pitch of the raw-channel tile: TMA boxes start at x0-4 (16-byte aligned coordinate)
 constexpr int XCP = PW + 4;      // pitch (32-bit words) of a packed raw-channel plane row: words PW .. PW + 3 are zero (unused mma k-slots read them)
@@ -59,7 +61,7 @@ constexpr int MAX_POOL = 16;
 constexpr int MAX_CONV = 8;
 constexpr int SMEM_MAX = 200 * 1024;   // beyond this the generic kernel takes the configuration (shipped ones need ~100 KB: 2 CTAs / SM)
 constexpr int WB_BYTES = 6 * 2 * 32 * 8;
-static_assert(PH % LV == 0 && PW % LH == 0 && TH % 2 == 0, "tiling");
+static_assert(PH % 6 == 0 && PH % 9 == 0 && PW % LH == 0 && TH % 2 == 0, "tiling");
 
 struct PoolSpec {            // canonical plane order: min pools by ascending radius, then max pools by ascending radius
     int n_pool, n_min;
@@ -238,13 +240,14 @@ __device__ __forceinline__ void build_weight_image(const WeightSrc& ws, uint8_t*
 
 __global__ void s2d_pack_weights_kernel(const WeightSrc ws, uint8_t* dst) { build_weight_image(ws, dst, threadIdx.x, blockDim.x); }
 
-// ---- pass 1: vertical nested-window sweep of one tile column, LV = 7 rows per thread -----------------------------------
+// ---- pass 1: vertical nested-window sweep of one tile column, LV rows per thread ---------------------------------------------
 // MINM / MAXM >= 0: the pool configuration is a compile-time constant (bit r set <=> a pool of radius r), so every mask test,
 // plane index and radius loop below folds away; -1: taken from the launch parameters (any configuration).
 // Each thread loads only the rows its largest radius needs (RMIN rows either side for the min pools, RMAX for the max pools).
 template <int R, bool BORDER, int MINM, int MAXM>
 __device__ __forceinline__ void pass1(const FastParams& p, const float* s_z, float* s_V, int j, int seg, int gy0, int gx0) {
     constexpr int ZW = PW + 2 * R, ZP = ZW + 4;
+    constexpr int LV = lv_of(R);
     constexpr int NV = LV + 2 * R;
     constexpr bool SPEC = MINM >= 0;
     const float INF = __int_as_float(0x7f800000);
@@ -532,12 +535,12 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     //         channels of the 3x3 conv input to packed bf16 -------------------------------------------------------------
     const bool border = gy0 < 0 || gx0 < 0 || gy0 + ZH > H || gx0 + ZW > W;
     {
-        constexpr int N_P1 = 2 * ZW;                       // work items of pass 1
+        constexpr int N_P1 = (PH / lv_of(R)) * ZW;                       // work items of pass 1
         constexpr int T_P1 = ((N_P1 + 31) / 32) * 32;      // ... rounded up to whole warps
         static_assert(T_P1 < NT, "pass 1 leaves no warp for the raw-channel split");
         if (tid < T_P1) {
             if (tid < N_P1) {
-                const int seg = tid >= ZW ? 1 : 0, j = tid - seg * ZW;
+                const int seg = tid / ZW, j = tid - seg * ZW;
                 if (border) pass1<R, true, MINM, MAXM>(p, s_z, s_V, j, seg, gy0, gx0);
                 else        pass1<R, false, MINM, MAXM>(p, s_z, s_V, j, seg, gy0, gx0);
             }
