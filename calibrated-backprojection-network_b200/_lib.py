@@ -8,8 +8,14 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libkbnet_b200.so')
 
-EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_set_autotune', 'kbnet_upconv2x_supported', 'kbnet_upconv2x_prepare_weights', 'kbnet_upconv2x_forward', 'kbnet_outlier_removal_forward', 'kbnet_conv3x3_depth_head_forward', 'kbnet_conv3x3_small_supported', 'kbnet_conv3x3_small_forward', 'kbnet_depth_u16_decode', 'kbnet_depth_u16_encode', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward',
+EXPORTS = ('kbnet_version', 'kbnet_last_error', 'kbnet_launch_count', 'kbnet_tma_engine_launch_count', 'kbnet_set_autotune', 'kbnet_upconv2x_supported', 'kbnet_upconv2x_prepare_weights', 'kbnet_upconv2x_forward', 'kbnet_outlier_removal_forward', 'kbnet_conv3x3_depth_head_forward', 'kbnet_conv3x3_small_supported', 'kbnet_conv3x3_small_forward', 'kbnet_depth_u16_decode', 'kbnet_depth_u16_encode', 'kbnet_s2d_forward', 'kbnet_s2d_wpack_bytes', 'kbnet_s2d_pack_weights', 'kbnet_kb_workspace_bytes', 'kbnet_kb_forward', 'kbnet_kb_forward_of', 'kbnet_kb_operand_format_supported',
+           'kbnet_operand_format_bytes', 'kbnet_to_operand_format', 'kbnet_from_operand_format', 'kbnet_conv3x3_small_forward_of',
            'kbnet_conv2d_forward', 'kbnet_depth_head_forward', 'kbnet_conv_wpack_bytes', 'kbnet_conv_pack_weights', 'kbnet_intrinsics_inverse')
+
+
+class KBNetKbOperandFormat(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ('image_hi', 'image_lo', 'fused_hi', 'fused_lo', 'out_image_hi', 'out_image_lo',
+                                               'out_fused_hi', 'out_fused_lo')]
 
 
 class KBNetConvSrc(ctypes.Structure):
@@ -51,6 +57,16 @@ def load():
     lib.kbnet_conv_pack_weights.argtypes = [vp, c.POINTER(i), i, i, i, vp, vp]
     lib.kbnet_kb_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp, i, vp, vp, vp, f,
                                      vp, ll, vp, ll, vp, ll, vp, sz, vp]
+    lib.kbnet_kb_forward_of.restype = i
+    lib.kbnet_kb_forward_of.argtypes = lib.kbnet_kb_forward.argtypes[:-1] + [c.POINTER(KBNetKbOperandFormat), vp]
+    lib.kbnet_kb_operand_format_supported.restype = i
+    lib.kbnet_kb_operand_format_supported.argtypes = [i] * 8
+    lib.kbnet_operand_format_bytes.restype = sz
+    lib.kbnet_operand_format_bytes.argtypes = [i] * 5
+    lib.kbnet_to_operand_format.restype = i
+    lib.kbnet_to_operand_format.argtypes = [vp, ll, i, i, i, i, vp, vp, i, vp]
+    lib.kbnet_from_operand_format.restype = i
+    lib.kbnet_from_operand_format.argtypes = [vp, vp, i, i, i, i, vp, ll, vp]
     lib.kbnet_conv2d_forward.restype = i
     lib.kbnet_conv2d_forward.argtypes = [c.POINTER(KBNetConvSrc), i, i, i, i, vp, vp, i, i, i, i, f, vp, ll, vp]
     lib.kbnet_upconv2x_supported.restype = i
@@ -69,6 +85,8 @@ def load():
     lib.kbnet_conv3x3_small_supported.argtypes = [i, i, i, i]
     lib.kbnet_conv3x3_small_forward.restype = i
     lib.kbnet_conv3x3_small_forward.argtypes = [vp, ll, i, i, i, i, vp, i, i, f, vp, ll, vp]
+    lib.kbnet_conv3x3_small_forward_of.restype = i
+    lib.kbnet_conv3x3_small_forward_of.argtypes = [vp, ll, i, i, i, i, vp, i, i, f, vp, ll, vp, vp, vp]
     lib.kbnet_depth_u16_decode.restype = i
     lib.kbnet_depth_u16_decode.argtypes = [vp, ll, vp, vp, vp]
     lib.kbnet_depth_u16_encode.restype = i

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libkbnet_b200.so')
-SOURCES = ['api.cu', 's2d_fused.cu', 's2d_generic.cu', 'conv_direct.cu', 'conv_umma.cu', 'conv_tma.cu', 'outlier.cu', 'conv_small.cu', 'conv_mma.cu', 'depth_io.cu']
+SOURCES = ['api.cu', 's2d_fused.cu', 's2d_generic.cu', 'conv_direct.cu', 'conv_umma.cu', 'conv_tma.cu', 'outlier.cu', 'conv_small.cu', 'conv_mma.cu', 'depth_io.cu', 'operand_format.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-shared', '--threads', '0']
 
 
 def _nvcc():

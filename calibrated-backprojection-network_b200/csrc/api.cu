@@ -84,16 +84,28 @@ size_t kbnet_kb_workspace_bytes(int N, int C_i, int C_d, int C_f, int H, int W, 
     return (((size_t)N * Ho * Wo * sizeof(float)) + 255) & ~(size_t)255;  // z at even pixels
 }
 
-int kbnet_kb_forward(const float* image, long long image_stride_n, const float* depth, long long depth_stride_n,
-                     const float* fused, long long fused_stride_n, const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_image, int F_i, const float* w_depth,
-                     int F_d, const float* w_proj, const float* w_fused, int F_f, const void* wpack_image,
-                     const void* wpack_depth, const void* wpack_fused, float neg_slope, float* out_image,
-                     long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
-                     long long out_fused_stride_n, void* workspace, size_t workspace_bytes, void* stream_) {
+int kbnet_kb_forward_of(const float* image, long long image_stride_n, const float* depth, long long depth_stride_n,
+                        const float* fused, long long fused_stride_n, const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_image, int F_i, const float* w_depth,
+                        int F_d, const float* w_proj, const float* w_fused, int F_f, const void* wpack_image,
+                        const void* wpack_depth, const void* wpack_fused, float neg_slope, float* out_image,
+                        long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
+                        long long out_fused_stride_n, void* workspace, size_t workspace_bytes, const kbnet_kb_operand_format* of, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (N == 0) return 0;
-    KB_CHECK_ARG(image && depth && w_image && w_depth && w_proj && w_fused && out_image && out_depth && out_fused,
-                 "kb: null pointer argument");
+    const bool image_of = of && of->image_hi && of->image_lo, fused_of = of && of->fused_hi && of->fused_lo;
+    const bool out_image_of = of && of->out_image_hi && of->out_image_lo, out_fused_of = of && of->out_fused_hi && of->out_fused_lo;
+    KB_CHECK_ARG((image || image_of) && depth && w_image && w_depth && w_proj && w_fused && out_depth && out_fused, "kb: null pointer argument");
+    if (of) {
+        KB_CHECK_ARG((of->image_hi != nullptr) == (of->image_lo != nullptr) && (of->fused_hi != nullptr) == (of->fused_lo != nullptr) &&
+                     (of->out_image_hi != nullptr) == (of->out_image_lo != nullptr) && (of->out_fused_hi != nullptr) == (of->out_fused_lo != nullptr),
+                     "kb: an operand-format tensor needs both its hi and its lo half");
+        const uintptr_t all = (uintptr_t)of->image_hi | (uintptr_t)of->image_lo | (uintptr_t)of->fused_hi | (uintptr_t)of->fused_lo |
+                              (uintptr_t)of->out_image_hi | (uintptr_t)of->out_image_lo | (uintptr_t)of->out_fused_hi | (uintptr_t)of->out_fused_lo;
+        if (all & 15) { set_error("kb: operand-format buffers must be 16-byte aligned"); return KBNET_E_ALIGN; }
+        KB_CHECK_ARG(!fused_of || (C_f > 0 && C_f % 8 == 0), "kb: operand-format `fused` needs C_f %% 8 == 0 (C_f = %d)", C_f);
+        KB_CHECK_ARG((!out_image_of || F_i % 8 == 0) && (!out_fused_of || F_f % 8 == 0), "kb: operand-format outputs need F %% 8 == 0");
+    }
+    if (fused_of && !fused) fused = depth;   // never dereferenced by the fused program; keeps the C_f / pointer contract below
     KB_CHECK_ARG((coordinates != nullptr) != (kinv != nullptr), "kb: pass exactly one of `coordinates` and `kinv`");
     KB_CHECK_ARG((fused != nullptr) == (C_f > 0), "kb: fused pointer and C_f=%d disagree", C_f);
     KB_CHECK_ARG((wpack_image != nullptr) == (wpack_depth != nullptr) && (wpack_image != nullptr) == (wpack_fused != nullptr),
@@ -101,17 +113,24 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
     KB_CHECK_ARG(N >= 0 && C_i > 0 && C_d > 0 && H > 0 && W > 0 && F_i > 0 && F_d > 0 && F_f > 0, "kb: bad shape");
     if (N == 0) return 0;
     const long long plane = (long long)H * W;
-    KB_CHECK_ARG(image_stride_n >= C_i * plane && depth_stride_n >= C_d * plane && (!fused || fused_stride_n >= C_f * plane),
+    KB_CHECK_ARG((!image || image_stride_n >= C_i * plane) && depth_stride_n >= C_d * plane && (!fused || fused_of || fused_stride_n >= C_f * plane),
                  "kb: input stride_n smaller than C*H*W");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    KB_CHECK_ARG(out_image_stride_n >= (long long)F_i * Ho * Wo && out_depth_stride_n >= (long long)F_d * Ho * Wo &&
+    KB_CHECK_ARG((!out_image || out_image_stride_n >= (long long)F_i * Ho * Wo) && out_depth_stride_n >= (long long)F_d * Ho * Wo &&
                  out_fused_stride_n >= (long long)F_f * Ho * Wo, "kb: output stride_n smaller than F*Ho*Wo");
     // the whole block as ONE fused launch (conv_tma.cu) whenever the tensors can be described to TMA
     if (wpack_image && kb_fused_supported(image, image_stride_n, depth, depth_stride_n, fused, fused_stride_n, coordinates, C_i, C_d, C_f, H, W,
                                           F_i, F_d, F_f))
+    {
+        KbOperandFormat kof;
+        if (of) memcpy(&kof, of, sizeof(kof));
+        static_assert(sizeof(KbOperandFormat) == sizeof(kbnet_kb_operand_format), "operand-format structs must match");
         return kb_fused_launch(image, image_stride_n, depth, depth_stride_n, fused, fused_stride_n, coordinates, kinv, N, C_i, C_d, C_f, H, W,
                                w_proj, wpack_image, F_i, wpack_depth, F_d, wpack_fused, F_f, neg_slope, out_image, out_image_stride_n,
-                               out_depth, out_depth_stride_n, out_fused, out_fused_stride_n, stream);
+                               out_depth, out_depth_stride_n, out_fused, out_fused_stride_n, stream, of ? &kof : nullptr);
+    }
+    KB_CHECK_ARG(!(image_of || fused_of || out_image_of || out_fused_of),
+                 "kb: the operand-format side channel needs the fused one-launch program (packed weights, C_i %% 16 == 0, C_d %% 16 == 0, W %% 4 == 0)");
     const size_t need = kbnet_kb_workspace_bytes(N, C_i, C_d, C_f, H, W, F_i, F_d, F_f);
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("kb: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
@@ -120,7 +139,7 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
     float* z = (float*)workspace;
     int rc;
     // conv_image = leaky(conv3x3 s2 (image))                                     net_utils.py:1348
-    {
+    if (out_image) {
         ConvParams p; memset(&p, 0, sizeof(p));
         p.n_src = 1;
         p.src[0] = make_src(image, nullptr, C_i, H, W, image_stride_n, SRC_DIRECT);
@@ -152,6 +171,43 @@ int kbnet_kb_forward(const float* image, long long image_stride_n, const float* 
         if ((rc = conv_launch(p, wpack_fused, stream))) return rc;
     }
     return 0;
+}
+
+int kbnet_kb_forward(const float* image, long long image_stride_n, const float* depth, long long depth_stride_n,
+                     const float* fused, long long fused_stride_n, const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_image, int F_i, const float* w_depth,
+                     int F_d, const float* w_proj, const float* w_fused, int F_f, const void* wpack_image,
+                     const void* wpack_depth, const void* wpack_fused, float neg_slope, float* out_image,
+                     long long out_image_stride_n, float* out_depth, long long out_depth_stride_n, float* out_fused,
+                     long long out_fused_stride_n, void* workspace, size_t workspace_bytes, void* stream) {
+    KB_CHECK_ARG(out_image || N == 0, "kb: null pointer argument");
+    return kbnet_kb_forward_of(image, image_stride_n, depth, depth_stride_n, fused, fused_stride_n, coordinates, kinv, N, C_i, C_d, C_f, H, W,
+                               w_image, F_i, w_depth, F_d, w_proj, w_fused, F_f, wpack_image, wpack_depth, wpack_fused, neg_slope, out_image,
+                               out_image_stride_n, out_depth, out_depth_stride_n, out_fused, out_fused_stride_n, workspace, workspace_bytes,
+                               nullptr, stream);
+}
+
+int kbnet_kb_operand_format_supported(int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f) {
+    if (C_i <= 0 || C_d <= 0 || C_f < 0 || H <= 0 || W <= 0 || F_i <= 0 || F_d <= 0 || F_f <= 0) return 0;
+    const float* aligned = reinterpret_cast<const float*>(uintptr_t(256));   // alignment stand-in, never dereferenced
+    if ((H & 1) || (W & 1)) return 0;   // parity planes of equal size
+    return kb_fused_supported(aligned, (long long)C_i * H * W, aligned, (long long)C_d * H * W, C_f ? aligned : nullptr, (long long)C_f * H * W,
+                              nullptr, C_i, C_d, C_f, H, W, F_i, F_d, F_f) ? 1 : 0;
+}
+
+size_t kbnet_operand_format_bytes(int N, int C, int H, int W, int even_pixels_only) {
+    if (N <= 0 || C <= 0 || (C & 7) || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return 0;
+    return (size_t)N * (size_t)(C / 8) * (size_t)(even_pixels_only ? 1 : 4) * (size_t)(H / 2) * (size_t)(W / 2) * 16;
+}
+
+int kbnet_to_operand_format(const float* x, long long x_stride_n, int N, int C, int H, int W, void* of_hi, void* of_lo, int even_pixels_only,
+                            void* stream) {
+    if (N == 0) return 0;
+    return to_operand_format_launch(x, x_stride_n, N, C, H, W, of_hi, of_lo, even_pixels_only, (cudaStream_t)stream);
+}
+
+int kbnet_from_operand_format(const void* of_hi, const void* of_lo, int N, int C, int H, int W, float* x, long long x_stride_n, void* stream) {
+    if (N == 0) return 0;
+    return from_operand_format_launch(of_hi, of_lo, N, C, H, W, x, x_stride_n, (cudaStream_t)stream);
 }
 
 size_t kbnet_conv_wpack_bytes(const int* src_channels, int n_src, int F, int ksize) {
@@ -207,12 +263,18 @@ int kbnet_conv3x3_small_supported(int C, int F, int ksize, int stride) { return 
 
 int kbnet_conv3x3_small_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
                                 float neg_slope, float* y, long long y_stride_n, void* stream) {
+    KB_CHECK_ARG(y || N == 0, "conv3x3_small: bad argument");
+    return kbnet_conv3x3_small_forward_of(x, x_stride_n, N, C, H, W, w, F, act, neg_slope, y, y_stride_n, nullptr, nullptr, stream);
+}
+
+int kbnet_conv3x3_small_forward_of(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
+                                   float neg_slope, float* y, long long y_stride_n, void* of_hi, void* of_lo, void* stream) {
     if (N == 0) return 0;
-    KB_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv3x3_small: bad argument");
+    KB_CHECK_ARG(x && w && (y || (of_hi && of_lo)) && N > 0 && H > 0 && W > 0, "conv3x3_small: bad argument");
     KB_CHECK_ARG(conv_mma_supported(C, F, 3, 1), "conv3x3_small: C=%d F=%d unsupported (C <= 4 and F <= 48, or C <= 16 and F <= 16)", C, F);
     KB_CHECK_ARG(act == 0 || (act == 1 && neg_slope >= 0.f && neg_slope <= 1.f), "conv3x3_small: act=%d neg_slope=%g unsupported", act, (double)neg_slope);
-    KB_CHECK_ARG(x_stride_n >= (long long)C * H * W && y_stride_n >= (long long)F * H * W, "conv3x3_small: stride_n too small");
-    return conv_mma_launch(x, x_stride_n, N, C, H, W, w, F, act, neg_slope, y, y_stride_n, (cudaStream_t)stream);
+    KB_CHECK_ARG(x_stride_n >= (long long)C * H * W && (!y || y_stride_n >= (long long)F * H * W), "conv3x3_small: stride_n too small");
+    return conv_mma_launch(x, x_stride_n, N, C, H, W, w, F, act, neg_slope, y, y_stride_n, (cudaStream_t)stream, of_hi, of_lo);
 }
 
 /* nearest-2x upsample + 3x3 conv as four source-resolution 2x2 convolutions (csrc/conv_tma.cu) */

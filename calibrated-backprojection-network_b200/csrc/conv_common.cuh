@@ -77,13 +77,22 @@ int upconv2x_prepare_weights(const float* w, int F, int C, float* out4, cudaStre
 int upconv2x_launch(const ConvSrcDev& src, int N, const void* const* wpack4, int F, int act, float slope, float* out, long long out_stride_n,
                     cudaStream_t stream);
 int conv_v2_launch(const ConvParams& p, const void* wpack, cudaStream_t stream);
+// optional operand-format side channel of the fused KB block (operand_format.cu): `image` as bf16 hi / lo parity planes
+// [N][C/8][4][H/2][W/2] x 16-byte entries, `fused` as its even pixels [N][C/8][H/2][W/2]; the same forms of conv_image /
+// conv_fused (even pixels) for the next block
+struct KbOperandFormat {
+    const void* image_hi; const void* image_lo;
+    const void* fused_hi; const void* fused_lo;
+    void* out_image_hi; void* out_image_lo;
+    void* out_fused_hi; void* out_fused_lo;
+};
 bool kb_fused_supported(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
                         const float* coordinates, int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);
 int kb_fused_launch(const float* image, long long image_sn, const float* depth, long long depth_sn, const float* fused, long long fused_sn,
                     const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_proj,
                     const void* wpack_image, int F_i, const void* wpack_depth, int F_d, const void* wpack_fused, int F_f, float slope,
                     float* out_image, long long out_image_sn, float* out_depth, long long out_depth_sn, float* out_fused, long long out_fused_sn,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const KbOperandFormat* of = nullptr);
 inline int conv_launch(const ConvParams& p, const void* wpack, cudaStream_t stream) {
     // no packed weights (fp32 mode), or a layer outside both tensor-core envelopes: the exact-fp32 CUDA-core kernel
     if (!wpack || (!conv_v2_supported(p) && !conv_umma_supported(p))) return conv_direct_launch(p, stream);
@@ -99,7 +108,10 @@ int conv_small_launch(const float* x, long long x_stride_n, int N, int C, int H,
                       float head_ratio, float* out, long long out_stride_n, cudaStream_t stream);
 bool conv_mma_supported(int C, int F, int ksize, int stride);
 int conv_mma_launch(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act, float slope, float* out,
-                    long long out_stride_n, cudaStream_t stream);
+                    long long out_stride_n, cudaStream_t stream, void* of_hi = nullptr, void* of_lo = nullptr);
+int to_operand_format_launch(const float* x, long long x_stride_n, int N, int C, int H, int W, void* of_hi, void* of_lo, int even_only,
+                             cudaStream_t stream);
+int from_operand_format_launch(const void* of_hi, const void* of_lo, int N, int C, int H, int W, float* x, long long x_stride_n, cudaStream_t stream);
 int depth_u16_decode_launch(const uint16_t* z16, long long n, float* depth, float* validity, cudaStream_t stream);
 int depth_u16_encode_launch(const float* depth, long long n, uint32_t* out, cudaStream_t stream);
 int depth_head_launch(const float* x, long long n, double min_d, double max_d, float* y, cudaStream_t stream);

@@ -46,6 +46,10 @@ struct MmaConvParams {
     int act;
     float slope;
     int use_tma;
+    // optional operand-format copy of the output (bf16 hi / lo, [N][F/8][4 parity planes][H/2][W/2] x 16-byte entries) for a following KB block;
+    // `out` may be null when only this copy is wanted
+    uint8_t* of_hi;
+    uint8_t* of_lo;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -264,6 +268,12 @@ __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__
         for (int j = 0; j < NTW; ++j)
             optr[j] = p.out + (size_t)n * p.out_stride_n + (size_t)(8 * (nt0 + j) + 2 * t) * plane + (size_t)(y0 + row0) * W + gxa;
         const bool full = y0 + TH <= H && x0 + TW <= W && (W & 1) == 0 && ((uintptr_t)p.out & 7) == 0 && (p.out_stride_n & 1) == 0;
+        const bool want_nchw = p.out != nullptr, want_of = p.of_hi != nullptr;
+        const int of_cg = (F + 7) >> 3;
+        // operand-format entry of (chunk, parity plane, y / 2, x / 2): 16 bytes; this lane owns bytes [4t, 4t + 4) of the entries of
+        // its two pixels, which sit in the even-column and the odd-column plane of the row's parity (H and W are even)
+        const size_t of_plane = (size_t)(H >> 1) * (W >> 1) * 16;
+        const size_t of_base = want_of ? ((size_t)n * of_cg + nt0) * 4 * of_plane + (size_t)(gxa >> 1) * 16 + 4 * t : 0;
         const bool in_a = gxa < W, in_b = gxa + 1 < W;
         float acc[3][NTW][4];                                 // the three open output rows
 #pragma unroll
@@ -302,6 +312,16 @@ __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__
                     float* d0 = optr[j];
                     float* d1 = d0 + plane;
                     optr[j] += W;
+                    if (want_of && y0 + row0 + li < H && f0 < F) {
+                        uint32_t h0, l0, h1, l1;
+                        split_rn(v0, v1, h0, l0);             // pixel gxa: filters f0, f0 + 1
+                        split_rn(v2, v3, h1, l1);             // pixel gxa + 1
+                        const int y = y0 + row0 + li;
+                        const size_t e = of_base + ((size_t)j * 4 + (size_t)(y & 1) * 2) * of_plane + (size_t)(y >> 1) * (size_t)(W >> 1) * 16;
+                        if (in_a) { *reinterpret_cast<uint32_t*>(p.of_hi + e) = h0; *reinterpret_cast<uint32_t*>(p.of_lo + e) = l0; }
+                        if (in_b) { *reinterpret_cast<uint32_t*>(p.of_hi + e + of_plane) = h1; *reinterpret_cast<uint32_t*>(p.of_lo + e + of_plane) = l1; }
+                    }
+                    if (!want_nchw) continue;
                     if (full && f0 + 1 < F) {
                         *reinterpret_cast<float2*>(d0) = make_float2(v0, v2);
                         *reinterpret_cast<float2*>(d1) = make_float2(v1, v3);
@@ -373,11 +393,16 @@ bool conv_mma_supported(int C, int F, int ksize, int stride) {
 }
 
 int conv_mma_launch(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act, float slope, float* out,
-                    long long out_stride_n, cudaStream_t stream) {
+                    long long out_stride_n, cudaStream_t stream, void* of_hi, void* of_lo) {
     KB_CHECK_ARG(conv_mma_supported(C, F, 3, 1), "conv_mma: C=%d F=%d unsupported", C, F);
+    KB_CHECK_ARG((of_hi != nullptr) == (of_lo != nullptr) &&
+                 (of_hi == nullptr || ((F & 7) == 0 && (((uintptr_t)of_hi | (uintptr_t)of_lo) & 15) == 0 && !(H & 1) && !(W & 1))),
+                 "conv_mma: the operand-format output needs both halves, 16-byte alignment, F %% 8 == 0 and even H, W");
+    KB_CHECK_ARG(out != nullptr || of_hi != nullptr, "conv_mma: no output");
     MmaConvParams p;
     p.x = x; p.x_stride_n = x_stride_n; p.w = w; p.out = out; p.out_stride_n = out_stride_n;
     p.N = N; p.C = C; p.H = H; p.W = W; p.F = F; p.act = act; p.slope = slope;
+    p.of_hi = (uint8_t*)of_hi; p.of_lo = (uint8_t*)of_lo;
     if (C <= 4) {
         if (F <= 16) return launch<4, 1, 1, true>(p, stream);
         if (F <= 32) return launch<4, 1, 2, true>(p, stream);

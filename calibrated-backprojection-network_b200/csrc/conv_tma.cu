@@ -45,7 +45,7 @@ namespace {
 constexpr int V2_MAX_STAGES = 72;
 constexpr int V2_MAX_CONVS = 4;
 constexpr int V2_MAX_USES = 4;
-constexpr int V2_MAX_MAPS = 4;
+constexpr int V2_MAX_MAPS = 8;   // 0-3: fp32 NCHW sources (4-D maps); 4-7: operand-format sources (5-D maps: hi, lo per tensor)
 // converter warps (a multiple of 4: the epilogue warps sit at conv_warps + 4 .. + 7 and address TMEM lane quarter warp % 4).
 // 12 warps were measured for the stride-2 programs (they fit: ~80 registers) and changed nothing -- the KB block is bound by the
 // latency chain raw TMA -> convert -> MMA -> commit of its two operand stages, not by converter throughput.
@@ -57,7 +57,8 @@ constexpr int V2_SMEM_LIMIT = 227 * 1024;
 constexpr int V2_MAX_ZC = 256;  // channels of the z projection
 
 enum { G_S1K3 = 0, G_S1K1 = 1, G_S2K3 = 2, G_S2K1 = 3 };
-enum { CK_NONE = 0, CK_TMA = 1, CK_TMA_P0 = 2, CK_COORDS = 3, CK_XYZ = 4, CK_XYZ_T = 5 };
+enum { CK_NONE = 0, CK_TMA = 1, CK_TMA_P0 = 2, CK_COORDS = 3, CK_XYZ = 4, CK_XYZ_T = 5,
+       CK_OF = 6, CK_OF_P0 = 7 };   // operand-format sources: TMA straight into the operand planes (all four parity planes / plane 0 only)
 constexpr uint16_t TAPS_ALL9 = 0x1FF, TAPS_ONE = 0x001, TAPS_CENTER = 0x010;  // bit t = tap (ky, kx) = (t / 3, t % 3) of the launch geometry
 
 struct V2Chunk {
@@ -85,8 +86,24 @@ struct V2Conv {
     // output addressing: out + n * out_stride_n + f * oplane + o_off + oy * o_row_pitch + ox * o_col_mul   (oy, ox on the launch grid)
     long long oplane, o_off;
     int o_row_pitch, o_col_mul;
+    // optional operand-format copy of the output for the next layer (operand_format.cu): 16-byte entries (8 filters, bf16) in a hi
+    // and a lo tensor, [N][of_cg][4 parity planes][Hout/2][Wout/2], or with of_even only the even pixels [N][of_cg][Hout/2][Wout/2];
+    // `out` may be null when only this copy is wanted
+    uint8_t* of_hi;
+    uint8_t* of_lo;
+    int of_cg, of_even;
 };
+// One entry of the MMA issuer's command table (built on the host for the chosen tile plan, read from the kernel parameters):
+// one tap of one convolution for all M-blocks of the tile.  The issuing thread does no bookkeeping beyond what the flags ask for.
+//   x = a_rel | flags << 16   a_rel: operand-plane offset of the tap (16-byte rows, relative to the A stage)
+//   y = b_rel | dcol << 16    b_rel: offset of the tap's weights inside the weight-ring slot (16-byte units); dcol: TMEM column
+//   z = instruction descriptor (N of this convolution's filter-split part; 2N in dual mode)
+enum { CMD_ACCUM = 1, CMD_WAIT_A = 2, CMD_COMMIT_A = 4, CMD_WAIT_W = 8, CMD_COMMIT_W = 16 };
+constexpr int V2_MAX_CMDS = 1152;
+
 struct V2Params {
+    uint4 cmd[V2_MAX_CMDS + 1];   // + one padding entry: the issuer prefetches command i + 1
+    int n_cmds, pad_cmd[3];
     V2Stage stage[V2_MAX_STAGES];
     V2Conv conv[V2_MAX_CONVS];
     int n_stages, n_convs, geo, dual;
@@ -103,6 +120,8 @@ struct V2Params {
     const float* kinv;    // [N, 9]   (CK_COORDS / CK_XYZ)
     const float* w_proj;  // [C_z]    (zacc)
     int C_z;
+    int has_of;           // some chunk is CK_OF / CK_OF_P0: warp CW + 3 runs the operand-format producer and arrives on every A_FULL
+    int of_box_bytes;     // bytes of one operand-format box = P * (R + 1) * 16
     long long* dbg;       // optional timeline buffer (KBNET_V2_TIMELINE): [role 0..4][4096] clock64 stamps of CTA 0
 };
 struct alignas(64) V2Maps {
@@ -118,6 +137,12 @@ static_assert(B_COUNT * 8 <= 512, "barrier area");
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
                  : "memory");
 }
 
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 
     if (tid == 0) {
         for (int i = 0; i < V2_MAX_RAW; ++i) { mbar_init(BAR(B_RAW_FULL + i), 1); mbar_init(BAR(B_RAW_EMPTY + i), CW); }
-        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), CW); mbar_init(BAR(B_A_EMPTY + i), 1); }
+        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), CW + (p.has_of ? 1 : 0)); mbar_init(BAR(B_A_EMPTY + i), 1); }
         for (int i = 0; i < V2_MAX_W; ++i) { mbar_init(BAR(B_W_FULL + i), 1); mbar_init(BAR(B_W_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACC_FULL + i), 1); mbar_init(BAR(B_ACC_EMPTY + i), 4); }
         fence_mbar_init();
@@ -253,6 +278,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                 for (int h = 0; h < 2; ++h) {
                     const V2Chunk ch = st.ch[h];
                     const int kind = ch.kind;
+                    if (kind == CK_OF || kind == CK_OF_P0) continue;   // lands in the operand planes by TMA (warp CW + 3)
                     const bool is_tma = kind == CK_TMA || kind == CK_TMA_P0 || kind == CK_XYZ_T;
                     const float* raw = nullptr;
                     int rslot = 0;
@@ -452,6 +478,48 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
             }
         }
         __syncwarp();
+    } else if (warp == CW + 3) {
+        // =================================================================================================================
+        // operand-format producer (one thread): chunks whose source already holds bf16 hi / lo 16-byte entries are loaded by TMA
+        // STRAIGHT into the operand planes of the A stage (a 5-D box with traversal stride 2 in x and y is one parity plane) --
+        // no raw ring, no converter work.  It arrives on A_FULL of every stage (with the byte count of its boxes, or plain).
+        // =================================================================================================================
+        if (p.has_of && elect_one()) {
+            Ring a_r;
+            const uint32_t plane_b = (uint32_t)p.plane_px * 16u;
+            const uint32_t box = (uint32_t)p.of_box_bytes;
+            for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
+                const TileCoord tc = decode_tile(p, tile);
+                const int x0c = tc.ox0 - 1, y0c = tc.oy0 - 1;   // G_S2K3: entry (0, 0) of every parity plane = plane pixel (ox0 - 1, oy0 - 1)
+                for (int s = 0; s < p.n_stages; ++s) {
+                    const V2Stage& st = p.stage[s];
+                    const int aslot = (int)a_r.slot;
+                    mbar_wait(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
+                    uint32_t nbox = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) nbox += st.ch[h].kind == CK_OF ? 8u : (st.ch[h].kind == CK_OF_P0 ? 2u : 0u);
+                    if (nbox) mbar_arrive_expect_tx(BAR(B_A_FULL + aslot), nbox * box);
+                    else      mbar_arrive(BAR(B_A_FULL + aslot));
+                    const uint32_t A = smem_u32(sA + (size_t)aslot * p.a_bytes);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const V2Chunk ch = st.ch[h];
+                        if (ch.kind != CK_OF && ch.kind != CK_OF_P0) continue;
+                        // CK_OF: the four parity planes of a full operand-format tensor (plane index = 4 * channel group + parity);
+                        // CK_OF_P0: plane 0 -- of a full tensor (cls 0) or of an even-pixel tensor (cls 1: one plane per channel group)
+                        const int npl = ch.kind == CK_OF ? 4 : 1;
+                        const int pl0 = ch.cls ? (int)(ch.c0 >> 3) : 4 * (int)(ch.c0 >> 3);
+                        for (int pl = 0; pl < npl; ++pl) {
+                            const uint32_t dst = A + (uint32_t)((pl * 4 + h) * p.plane_px) * 16u;
+                            tma_load_5d(dst, &maps.m[ch.tmap], 0, x0c, y0c, pl0 + pl, tc.n, BAR(B_A_FULL + aslot));
+                            tma_load_5d(dst + 2u * plane_b, &maps.m[ch.tmap + 1], 0, x0c, y0c, pl0 + pl, tc.n, BAR(B_A_FULL + aslot));
+                        }
+                    }
+                    a_r.advance((uint32_t)p.n_a);
+                }
+            }
+        }
+        __syncwarp();
     } else if (warp == CW + 2) {
         // =================================================================================================================
         // MMA issuer.  The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
@@ -459,103 +527,74 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
         // =================================================================================================================
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         Ring a_r, w_r, t_r;
-        int dbg_i = 0, dbg_t = 0, dbg_w = 0;
+        int dbg_i = 0, dbg_t = 0;
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // A: SBO = 128 B, descriptor version 1
-        const uint32_t b_hi512 = (512u >> 4) | (1u << 14), b_hi256 = (256u >> 4) | (1u << 14);  // B: SBO of hi-only / interleaved [hi|lo] rows
+        // B: SBO of hi-only rows (512 B) / interleaved [hi|lo] rows of the dual form (256 B)
+        const uint32_t b_desc_hi = DUAL ? ((256u >> 4) | (1u << 14)) : ((512u >> 4) | (1u << 14));
         const uint32_t b_lbo = (128u >> 4) << 16;                                  // B: LBO = 128 B between the two K chunks
-
         const uint32_t a_lbo = (((uint32_t)p.plane_px * 16u) >> 4) << 16;          // LBO: chunk 0 -> chunk 1 plane
         const uint32_t a_lo_off = (2u * (uint32_t)p.plane_px * 16u) >> 4;          // hi planes -> lo planes
         const uint32_t tile_cols = (uint32_t)(p.MB * p.cols_block);
         const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4;
         const uint32_t a_bytes16 = (uint32_t)p.a_bytes >> 4, w_bytes16 = (uint32_t)p.w_bytes >> 4;
         const uint32_t n_w = (uint32_t)p.n_w, n_a = (uint32_t)p.n_a, acc_bufs = (uint32_t)p.acc_bufs;
-        const int MB = p.MB;
+        const int MB = p.MB, n_cmds = p.n_cmds;
         const uint32_t cols_block = (uint32_t)p.cols_block;
-        constexpr bool dual = DUAL;
-        // operand-plane offset (in 16-byte rows) of tap t: a 3x3 tap is the same plane read from a shifted start address
-        const uint32_t P_u = (uint32_t)p.P, plane4 = 4u * (uint32_t)p.plane_px;
-        auto tap_offset = [&](uint32_t ky, uint32_t kx) -> uint32_t {
-            if (GEO == G_S1K3) return ky * P_u + kx;  // (tap 4 = the centre: P + 1)
-            if (GEO == G_S2K3)  // dy = ky - 1, dx = kx - 1: parity plane (dy != 0, dx != 0), shift (dy >= 0) * P + (dx >= 0)
-                return ((ky != 1u ? 2u : 0u) + (kx != 1u ? 1u : 0u)) * plane4 + (ky != 0u ? P_u : 0u) + (kx != 0u ? 1u : 0u);
-            return 0u;
-        };
-        // ONE elected lane runs the whole role: per-block elect/reconvergence costs ~190 clk on this path (tools/umma_rate_probe.cu),
-        // and inside an elect branch the compiler still keeps the (single-lane) values in uniform registers.
+        // ONE elected lane runs the whole role: per-block elect/reconvergence costs ~190 clk on this path (tools/umma_rate_probe.cu).
+        // The per-tap work is a table walk: the stage / use / tap / weight-slot structure of the program was flattened on the host
+        // (build_commands), because this single thread's scalar bookkeeping -- not the tensor pipe -- set the pace of the low-N layers
+        // (~60 instructions per tap for three MMAs; profiles/r02b_kb_timeline.txt).
         if (elect_one()) {
             for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
                 mbar_wait(BAR(B_ACC_EMPTY + t_r.slot), t_r.phase ^ 1u);
                 tc_fence_after();
                 V2_STAMP(4, dbg_t); ++dbg_t;
                 const uint32_t acc = tmem_u + t_r.slot * tile_cols;
-                for (int s = 0; s < p.n_stages; ++s) {
-                    const V2Stage& st = p.stage[s];
-                    mbar_wait(BAR(B_A_FULL + a_r.slot), a_r.phase);
-                    tc_fence_after();
-                    V2_STAMP(2, dbg_i); ++dbg_i;
-                    const uint32_t a_base16 = (sA16 + a_r.slot * a_bytes16) | a_lbo;
-                    for (int u = 0; u < st.n_use; ++u) {
-                        const V2Use us = st.use[u];
-                        const V2Conv& cv = p.conv[us.conv];
-                        const uint32_t nsl = (uint32_t)cv.Nsl;
-                        const uint32_t piece16 = nsl * 4u;                               // one tap of weights, in 16-byte units
-                        const uint32_t idesc1 = idesc_bf16_f32(128, (int)nsl), idesc2 = idesc_bf16_f32(128, (int)(2 * nsl));
-                        const uint32_t dcol = acc + (uint32_t)cv.col;
-                        // issue every M-block of one tap: weights at b16 (16-byte units, LBO already or-ed in)
-                        auto do_tap = [&](uint32_t off, uint32_t b16, uint32_t accum) {
-                            uint32_t a0 = a_base16 + off;
-                            uint32_t d = dcol;
-                            if (dual) {  // B' = [b_hi | b_lo] interleaved per 8-filter group (SBO 256 B): all four hi/lo products in two MMAs
+                uint32_t a_base16 = 0, b_base16 = 0;
+                uint4 nxt = p.cmd[0];
 #pragma unroll 1
-                                for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi256), idesc2, accum);
-                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi256), idesc2, 1u);
-                                }
-                            } else {
+                for (int i = 0; i < n_cmds; ++i) {
+                    const uint4 c = nxt;
+                    nxt = p.cmd[i + 1];
+                    const uint32_t flags = c.x >> 16;
+                    if (flags & CMD_WAIT_A) {
+                        mbar_wait(BAR(B_A_FULL + a_r.slot), a_r.phase);
+                        tc_fence_after();
+                        V2_STAMP(2, dbg_i); ++dbg_i;
+                        a_base16 = (sA16 + a_r.slot * a_bytes16) | a_lbo;
+                    }
+                    if (flags & CMD_WAIT_W) {
+                        mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
+                        b_base16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
+                    }
+                    uint32_t a0 = a_base16 + (c.x & 0xFFFFu);
+                    const uint32_t b16 = b_base16 + (c.y & 0xFFFFu);
+                    uint32_t d = acc + (c.y >> 16);
+                    const uint32_t idesc = c.z;
+                    const uint32_t accum = flags & CMD_ACCUM;
+                    if (DUAL) {  // B' = [b_hi | b_lo] interleaved per 8-filter group: all four hi/lo products in two MMAs
 #pragma unroll 1
-                                for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_hi512), idesc1, accum);
-                                    mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_hi512), idesc1, 1u);
-                                    mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16 + 16u, b_hi512), idesc1, 1u);
-                                }
-                            }
-                        };
-                        {
-                            const uint32_t mask = us.tapmask;
-                            int left = __popc(mask);
-                            const int Tu = left < p.T ? left : p.T;  // taps per weight-ring slot
-                            int cnt = 0;
-                            uint32_t b16 = 0, accum = us.first ? 0u : 1u;
+                        for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
+                            mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_desc_hi), idesc, accum);
+                            mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_desc_hi), idesc, 1u);
+                        }
+                    } else {
 #pragma unroll 1
-                            for (uint32_t ky = 0; ky < 3; ++ky) {  // rows rolled, columns unrolled: a third of the code of a full unroll
-#pragma unroll
-                                for (uint32_t kx = 0; kx < 3; ++kx) {
-                                    const uint32_t t = 3u * ky + kx;
-                                    if (!((mask >> t) & 1u)) continue;
-                                    if (cnt == 0) {
-                                        V2_STAMP(5, dbg_w); ++dbg_w;
-                                        mbar_wait(BAR(B_W_FULL + w_r.slot), w_r.phase);  // weights land through the async proxy: the barrier's acquire is enough
-                                        V2_STAMP(5, dbg_w); ++dbg_w;
-                                        b16 = (sW16 + w_r.slot * w_bytes16) | b_lbo;
-                                    }
-                                    do_tap(tap_offset(ky, kx), b16, accum);
-                                    accum = 1u;
-                                    b16 += piece16;
-                                    --left;
-                                    if (++cnt == Tu || left == 0) {
-                                        mma_commit(BAR(B_W_EMPTY + w_r.slot));
-                                        V2_STAMP(5, dbg_w); ++dbg_w;
-                                        w_r.advance(n_w);
-                                        cnt = 0;
-                                    }
-                                }
-                            }
+                        for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
+                            mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16, b_desc_hi), idesc, accum);
+                            mma_bf16_ss(d, make_desc(a0 + a_lo_off, desc_hi), make_desc(b16, b_desc_hi), idesc, 1u);
+                            mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16 + 16u, b_desc_hi), idesc, 1u);
                         }
                     }
-                    mma_commit(BAR(B_A_EMPTY + a_r.slot));
-                    V2_STAMP(2, dbg_i); ++dbg_i;
-                    a_r.advance(n_a);
+                    if (flags & CMD_COMMIT_W) {
+                        mma_commit(BAR(B_W_EMPTY + w_r.slot));
+                        w_r.advance(n_w);
+                    }
+                    if (flags & CMD_COMMIT_A) {
+                        mma_commit(BAR(B_A_EMPTY + a_r.slot));
+                        V2_STAMP(2, dbg_i); ++dbg_i;
+                        a_r.advance(n_a);
+                    }
                 }
                 mma_commit(BAR(B_ACC_FULL + t_r.slot));
                 t_r.advance(acc_bufs);
@@ -618,7 +657,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 #pragma unroll
                             for (int k = 0; k < 16; ++k) o[k] = leaky(o[k], p.slope);
                         }
-                        if (valid) {
+                        if (valid && cv.out != nullptr) {
                             float* d = dst;
                             if (c + 16 <= nf) {
 #pragma unroll
@@ -627,6 +666,19 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 #pragma unroll
                                 for (int k = 0; k < 16; ++k, d += oplane)
                                     if (c + k < nf) *d = o[k];
+                            }
+                        }
+                        // operand-format copy: 8 filters of this pixel = one 16-byte entry (hi) + one (lo) in the pixel's parity plane
+                        if (valid && cv.of_hi != nullptr && !(cv.of_even && ((oy | ox) & 1))) {
+                            const size_t of_plane = (size_t)(p.Hout >> 1) * (size_t)(p.Wout >> 1);
+                            const size_t pix = (size_t)(oy >> 1) * (size_t)(p.Wout >> 1) + (size_t)(ox >> 1);
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                if (c + 8 * hf < nf) {
+                                    const size_t cgi = (size_t)tc.n * cv.of_cg + (size_t)((f0 + c) >> 3) + hf;
+                                    const size_t e = (cv.of_even ? cgi * of_plane + pix : (cgi * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * of_plane + pix) * 16;
+                                    store_split8(cv.of_hi + e, cv.of_lo + e, reinterpret_cast<const float(&)[8]>(o[8 * hf]));
+                                }
                             }
                         }
                         dst += 16 * oplane;
@@ -682,6 +734,19 @@ bool make_map4(CUtensorMap* tm, const ConvSrcDev& s, int N, int bw, int bh, int 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// operand-format source (operand_format.cu): `planes` = 4 * channel groups (full tensor) or the channel groups (even-pixel tensor)
+// parity planes of H2 x W2 16-byte entries per sample: 5-D map {8 bf16, W2, H2, planes, N}; one box = P x R1 entries of one plane
+bool make_map_of(CUtensorMap* tm, const void* ptr, int N, int planes, int H2, int W2, int P, int R1) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || ptr == nullptr || ((uintptr_t)ptr & 15) || P > 256 || R1 > 256 || planes < 1 || H2 < 1 || W2 < 1) return false;
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)planes, (cuuint64_t)N};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)W2 * 16, (cuuint64_t)W2 * H2 * 16, (cuuint64_t)W2 * H2 * planes * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)P, (cuuint32_t)R1, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 double mma_cycles(int N) {  // measured with a lean single-lane issue loop, tools/umma_rate_probe.cu (profiles/r01_umma_rate_probe.log)
     const double c = N / 2.0, s = 44.0 + N / 6.0;
     return c > s ? c : s;
@@ -700,6 +765,8 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     else if (geo == G_S1K1) { p.P = TW; p.n_entries = R * p.P; max_shift = 0; p.BW[0] = TW; p.BH[0] = R; }
     else if (geo == G_S2K3) { p.P = TW + 1; p.n_entries = (R + 1) * p.P; max_shift = p.P + 1; p.BW[0] = roundup(2 * p.P + 2, 4); p.BH[0] = 2 * R + 2; }
     else { p.P = TW; p.n_entries = R * p.P; max_shift = 0; p.BW[0] = 2 * TW; p.BH[0] = 2 * R; }
+    if (p.has_of && (geo != G_S2K3 || p.P > 256 || R + 1 > 256)) return -1;   // one operand-format box = one parity plane
+    p.of_box_bytes = p.P * (R + 1) * 16;
     p.BW[1] = p.BH[1] = 4;
     if (has_up) { p.BW[1] = roundup(TW / 2 + 5, 4); p.BH[1] = R / 2 + 2; }
     if (geo == G_S2K3) { p.BW[1] = p.BW[0]; p.BH[1] = R + 1; }  // class 1 of the stride-2 programs: even rows only (sources read at even pixels)
@@ -817,12 +884,65 @@ std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks
 
 std::atomic<int> g_autotune{-1};  // -1: not initialised (KBNET_AUTOTUNE), 0 off, 1 on
 
+// Flatten the program (stages x uses x taps, weight-ring slots of p.T taps) into the MMA issuer's command table for the geometry
+// apply_geometry() has just set.  The weight producer walks the same (stage, use, slot) order.
+int build_commands(V2Params& p) {
+    const int geo = p.geo;
+    const uint32_t P_u = (uint32_t)p.P, plane4 = 4u * (uint32_t)p.plane_px;
+    // operand-plane offset (in 16-byte rows) of tap (ky, kx): a 3x3 tap is the same plane read from a shifted start address
+    auto tap_offset = [&](uint32_t ky, uint32_t kx) -> uint32_t {
+        if (geo == G_S1K3) return ky * P_u + kx;  // (tap 4 = the centre: P + 1)
+        if (geo == G_S2K3)  // dy = ky - 1, dx = kx - 1: parity plane (dy != 0, dx != 0), shift (dy >= 0) * P + (dx >= 0)
+            return ((ky != 1u ? 2u : 0u) + (kx != 1u ? 1u : 0u)) * plane4 + (ky != 0u ? P_u : 0u) + (kx != 0u ? 1u : 0u);
+        return 0u;
+    };
+    int n = 0;
+    for (int s = 0; s < p.n_stages; ++s) {
+        const V2Stage& st = p.stage[s];
+        const int first_cmd = n;
+        for (int u = 0; u < st.n_use; ++u) {
+            const V2Use& us = st.use[u];
+            const V2Conv& cv = p.conv[us.conv];
+            const uint32_t piece16 = (uint32_t)cv.Nsl * 4u;   // one tap of weights, in 16-byte units
+            const uint32_t idesc = idesc_bf16_f32(128, p.dual ? 2 * cv.Nsl : cv.Nsl);
+            int left = __builtin_popcount((unsigned)us.tapmask);
+            const int Tu = left < p.T ? left : p.T;
+            int cnt = 0;
+            uint32_t accum = us.first ? 0u : CMD_ACCUM;
+            for (uint32_t t = 0; t < 9; ++t) {
+                if (!((us.tapmask >> t) & 1u)) continue;
+                KB_CHECK_ARG(n < V2_MAX_CMDS, "conv(v2): program too long for the command table");
+                uint32_t flags = accum | (cnt == 0 ? CMD_WAIT_W : 0u);
+                const uint32_t a_rel = tap_offset(t / 3, t % 3), b_rel = (uint32_t)cnt * piece16;
+                KB_CHECK_ARG(a_rel < 0x10000u && b_rel < 0x10000u && cv.col < 0x10000, "conv(v2): command field overflow");
+                accum = CMD_ACCUM;
+                --left;
+                if (++cnt == Tu || left == 0) { flags |= CMD_COMMIT_W; cnt = 0; }
+                p.cmd[n++] = make_uint4(a_rel | (flags << 16), b_rel | ((uint32_t)cv.col << 16), idesc, 0u);
+            }
+        }
+        KB_CHECK_ARG(n > first_cmd, "conv(v2): stage %d has no taps", s);
+        p.cmd[first_cmd].x |= (uint32_t)CMD_WAIT_A << 16;
+        p.cmd[n - 1].x |= (uint32_t)CMD_COMMIT_A << 16;
+    }
+    p.cmd[n] = make_uint4(0u, 0u, 0u, 0u);
+    p.n_cmds = n;
+    return 0;
+}
+
 // geometry + rings + tensor maps + launch for one plan
+struct OfSrc {   // operand-format tensor: hi and lo halves of the bf16 split, `planes` parity planes of H2 x W2 entries per sample
+    const void* hi;
+    const void* lo;
+    int planes, H2, W2;
+};
+
 int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, int sms,
-                     cudaStream_t stream, bool report) {
+                     cudaStream_t stream, bool report, const OfSrc* of_src = nullptr, int n_of = 0) {
     const int geo = p.geo;
     long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
     KB_CHECK_ARG(used > 0 && used <= V2_SMEM_LIMIT, "conv(v2): plan R=%d TW=%d split=%d dual=%d does not fit", plan.R, plan.TW, plan.n_split, plan.dual);
+    if (int rc = build_commands(p)) return rc;
     p.n_raw = 2; p.n_a = 2; p.n_w = 2;
     // Spend the remaining shared memory on ring depth, in the order in which exposed latency was measured to cost (role timelines,
     // tools/v2_timeline.py): a raw slot is refilled only after the converters release it, so with 2 slots every chunk waits a full
@@ -848,9 +968,16 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
 
     V2Maps maps;
     memset(&maps, 0, sizeof(maps));
-    for (int i = 0; i < n_maps; ++i)
+    for (int i = 0; i < n_maps && i < 4; ++i)
         KB_CHECK_ARG(make_map4(&maps.m[i], map_src[i], p.N, p.BW[map_cls[i]], p.BH[map_cls[i]], (geo == G_S2K3 && map_cls[i] == 1) ? 2 : 1),
                      "conv(v2): cuTensorMapEncodeTiled failed for source %d", i);
+
+    for (int i = 0; i < n_of; ++i) {
+        KB_CHECK_ARG(4 + 2 * i + 1 < V2_MAX_MAPS, "conv(v2): too many operand-format sources");
+        KB_CHECK_ARG(make_map_of(&maps.m[4 + 2 * i], of_src[i].hi, p.N, of_src[i].planes, of_src[i].H2, of_src[i].W2, p.P, p.R + 1) &&
+                     make_map_of(&maps.m[5 + 2 * i], of_src[i].lo, p.N, of_src[i].planes, of_src[i].H2, of_src[i].W2, p.P, p.R + 1),
+                     "conv(v2): cuTensorMapEncodeTiled failed for operand-format source %d", i);
+    }
 
     const long long grid = p.n_tiles < sms ? p.n_tiles : sms;
     KB_CHECK_ARG(grid > 0, "conv(v2): empty grid");
@@ -901,17 +1028,21 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     return 0;
 }
 
-int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, cudaStream_t stream) {
+int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, cudaStream_t stream,
+              const OfSrc* of_src = nullptr, int n_of = 0) {
     const int geo = p.geo;
-    int n_ops = 0, n_tma_chunks = 0, n_chunks = 0;  // per tile
+    int n_ops = 0, n_tma_chunks = 0, n_chunks = 0, n_of_chunks = 0;  // per tile
     for (int s = 0; s < p.n_stages; ++s) {
         for (int h = 0; h < 2; ++h) {
             const int k = p.stage[s].ch[h].kind;
+            if (k == CK_OF || k == CK_OF_P0) { ++n_of_chunks; continue; }   // no converter work, no raw slot
             n_chunks += 1;
             if (k == CK_TMA || k == CK_TMA_P0 || k == CK_XYZ_T) ++n_tma_chunks;
         }
         for (int u = 0; u < p.stage[s].n_use; ++u) n_ops += __builtin_popcount((unsigned)p.stage[s].use[u].tapmask);
     }
+    p.has_of = n_of_chunks > 0;
+    KB_CHECK_ARG(!p.has_of || (geo == G_S2K3 && of_src != nullptr && n_of > 0), "conv(v2): operand-format chunks need a stride-2 3x3 program and their sources");
     int sms = 148;
     {
         int dev = 0;
@@ -928,7 +1059,7 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
         int* k = key.v;
         k[0] = geo; k[1] = p.N; k[2] = p.Hin; k[3] = p.Win; k[4] = p.Hout; k[5] = p.Wout; k[6] = p.n_stages; k[7] = p.n_convs;
         for (int j = 0; j < p.n_convs; ++j) { k[8 + j] = p.conv[j].Npad; k[12 + j] = p.conv[j].ntaps; }
-        k[16] = has_up; k[17] = n_chunks; k[18] = n_tma_chunks; k[19] = n_ops; k[20] = sms; k[21] = autotune != 0;
+        k[16] = has_up; k[17] = n_chunks; k[18] = n_tma_chunks; k[19] = n_ops; k[20] = sms; k[21] = autotune != 0; k[22] = n_of_chunks;
     }
     V2Plan plan = {0, 0, 0, 0};
     bool found = false;
@@ -950,12 +1081,12 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
             float best_ms = 1e30f;
             const size_t n_try = cands.size() < 12 ? cands.size() : 12;
             for (size_t i = 0; i < n_try; ++i) {
-                int rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);  // warm-up (I-cache, L2)
+                int rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false, of_src, n_of);  // warm-up (I-cache, L2)
                 if (rc) continue;
                 float cand_ms = 1e30f;
                 for (int rep = 0; rep < 3 && !rc; ++rep) {  // best of three: a single shot is too noisy to rank close candidates
                     KB_CUDA(cudaEventRecord(e0, stream));
-                    rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false);
+                    rc = launch_with_plan(p, cands[i].plan, map_src, n_maps, map_cls, has_up, sms, stream, false, of_src, n_of);
                     KB_CUDA(cudaEventRecord(e1, stream));
                     if (rc) break;
                     KB_CUDA(cudaEventSynchronize(e1));
@@ -976,7 +1107,7 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         if (g_plans.size() < 4096) g_plans.push_back({key, plan});
     }
-    return launch_with_plan(p, plan, map_src, n_maps, map_cls, has_up, sms, stream, true);
+    return launch_with_plan(p, plan, map_src, n_maps, map_cls, has_up, sms, stream, true, of_src, n_of);
 }
 
 // same grouping as conv_umma.cu / conv_pack_weights: every source is cut into chunks of <= 8 channels, padded to an even count
@@ -1011,7 +1142,7 @@ bool v2_disabled() {
 bool conv_v2_supported(const ConvParams& c) {
     if (v2_disabled()) return false;
     if (!((c.ksize == 3 || c.ksize == 1) && (c.stride == 1 || c.stride == 2))) return false;
-    if (c.n_src < 1 || c.n_src > V2_MAX_MAPS) return false;
+    if (c.n_src < 1 || c.n_src > 4) return false;   // fp32 sources use tensor maps 0-3
     const int Npad = (c.F + 15) & ~15;
     if (Npad > 1024) return false;
     for (int i = 0; i < c.n_src; ++i) {
@@ -1082,24 +1213,41 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
                     const float* coordinates, const float* kinv, int N, int C_i, int C_d, int C_f, int H, int W, const float* w_proj,
                     const void* wpack_image, int F_i, const void* wpack_depth, int F_d, const void* wpack_fused, int F_f, float slope,
                     float* out_image, long long out_image_sn, float* out_depth, long long out_depth_sn, float* out_fused, long long out_fused_sn,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const KbOperandFormat* of) {
     static thread_local V2Params q;
     memset(&q, 0, sizeof(q));
     q.geo = G_S2K3;
     q.N = N; q.Hin = H; q.Win = W; q.Hout = (H - 1) / 2 + 1; q.Wout = (W - 1) / 2 + 1;
     q.slope = slope; q.kinv = kinv; q.w_proj = w_proj; q.C_z = C_d;
-    q.n_convs = 3;
-    const void* packs[3] = {wpack_image, wpack_depth, wpack_fused};
-    float* outs[3] = {out_image, out_depth, out_fused};
-    const long long osn[3] = {out_image_sn, out_depth_sn, out_fused_sn};
-    const int Fs[3] = {F_i, F_d, F_f};
-    for (int j = 0; j < 3; ++j) {
+    const bool image_of = of && of->image_hi && of->image_lo;                 // image / fused arrive in operand format: TMA straight into
+    const bool fused_of = of && fused && of->fused_hi && of->fused_lo;        // the operand planes, no converter work for their chunks
+    const bool out_image_of = of && of->out_image_hi && of->out_image_lo;
+    // conv_image with no output at all is not computed (KBNetEncoder's last block: src/networks.py:476-523 only reads its shape);
+    // the image is then needed at even pixels only (conv_fused's centre tap)
+    const bool skip_image = out_image == nullptr && !out_image_of;
+    const int ci = skip_image ? -1 : 0, cd = skip_image ? 0 : 1, cf = skip_image ? 1 : 2;   // convolution slots
+    q.n_convs = skip_image ? 2 : 3;
+    auto set_conv = [&](int j, const void* pack, float* out, long long osn, int F, int ntaps) {
         V2Conv& cv = q.conv[j];
-        cv.wpack = (const uint8_t*)packs[j]; cv.out = outs[j]; cv.out_stride_n = osn[j];
-        cv.F = Fs[j]; cv.Npad = (Fs[j] + 15) & ~15; cv.act = 1; cv.ntaps = j == 2 ? 1 : 9;
+        cv.wpack = (const uint8_t*)pack; cv.out = out; cv.out_stride_n = osn;
+        cv.F = F; cv.Npad = (F + 15) & ~15; cv.act = 1; cv.ntaps = ntaps;
         cv.oplane = (long long)q.Hout * q.Wout; cv.o_off = 0; cv.o_row_pitch = q.Wout; cv.o_col_mul = 1;
+    };
+    if (!skip_image) set_conv(ci, wpack_image, out_image, out_image_sn, F_i, 9);
+    set_conv(cd, wpack_depth, out_depth, out_depth_sn, F_d, 9);
+    set_conv(cf, wpack_fused, out_fused, out_fused_sn, F_f, 1);
+    if (of) {   // operand-format copies of conv_image / conv_fused for the next block
+        KB_CHECK_ARG((!out_image_of || F_i % 8 == 0) && (!(of->out_fused_hi && of->out_fused_lo) || F_f % 8 == 0),
+                     "kb(v2): operand-format outputs need filter counts that are multiples of 8");
+        if (out_image_of) { q.conv[ci].of_hi = (uint8_t*)of->out_image_hi; q.conv[ci].of_lo = (uint8_t*)of->out_image_lo; q.conv[ci].of_cg = F_i / 8; }
+        if (of->out_fused_hi && of->out_fused_lo) {   // conv_fused: its even pixels only (all the next block reads)
+            q.conv[cf].of_hi = (uint8_t*)of->out_fused_hi; q.conv[cf].of_lo = (uint8_t*)of->out_fused_lo; q.conv[cf].of_cg = F_f / 8; q.conv[cf].of_even = 1;
+        }
+        KB_CHECK_ARG(!(image_of || fused_of) || (!(H & 1) && !(W & 1)), "kb(v2): operand-format sources need even H and W");
+        KB_CHECK_ARG(!(out_image_of || q.conv[cf].of_hi) || (!(q.Hout & 1) && !(q.Wout & 1)), "kb(v2): operand-format outputs need even Ho and Wo");
     }
-    // tensor maps: 0 image, 1 depth, 2 fused, 3 coordinates
+    KB_CHECK_ARG(out_depth != nullptr && out_fused != nullptr, "kb(v2): conv_depth / conv_fused need their NCHW outputs");
+    // tensor maps: 0 image, 1 depth, 2 fused, 3 coordinates (fp32 NCHW); 4/5 image, 6/7 fused in operand format
     ConvSrcDev srcs[V2_MAX_MAPS];
     memset(srcs, 0, sizeof(srcs));
     auto mk = [&](const float* ptr, int C, long long sn) {
@@ -1108,18 +1256,28 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
         s.ptr = ptr; s.C = C; s.H = H; s.W = W; s.stride_n = sn;
         return s;
     };
-    srcs[0] = mk(image, C_i, image_sn);
     srcs[1] = mk(depth, C_d, depth_sn);
-    srcs[2] = fused ? mk(fused, C_f, fused_sn) : srcs[0];
-    srcs[3] = coordinates ? mk(coordinates, 3, 3LL * H * W) : srcs[0];
-    const uint8_t map_cls[V2_MAX_MAPS] = {0, 0, 1, 0};  // `fused` is only read at even pixels: even-row boxes (half the traffic)
+    srcs[0] = image_of ? srcs[1] : mk(image, C_i, image_sn);               // unused maps still have to encode: point them at depth
+    srcs[2] = (fused && !fused_of) ? mk(fused, C_f, fused_sn) : srcs[1];
+    srcs[3] = coordinates ? mk(coordinates, 3, 3LL * H * W) : srcs[1];
+    // sources read at even pixels only (`fused`; the image when conv_image is skipped) use even-row boxes: half the traffic
+    const uint8_t map_cls[V2_MAX_MAPS] = {(uint8_t)(skip_image ? 1 : 0), 0, 1, 0};
+    OfSrc ofs[2];
+    memset(ofs, 0, sizeof(ofs));
+    int n_of = 0;
+    if (image_of || fused_of) {
+        n_of = 2;
+        const OfSrc img = {of->image_hi, of->image_lo, 4 * (C_i / 8), H / 2, W / 2}, fus = {of->fused_hi, of->fused_lo, C_f / 8, H / 2, W / 2};
+        ofs[0] = image_of ? img : fus;       // both map pairs must encode: an unused one aliases the other
+        ofs[1] = fused_of ? fus : img;
+    }
     int s = 0;
     // (1) depth chunks -> conv_depth (9 taps) and the z projection
     for (int j = 0; j < C_d / 16; ++j, ++s) {
         V2Stage& st = q.stage[s];
         for (int h = 0; h < 2; ++h) { st.ch[h].kind = CK_TMA; st.ch[h].tmap = 1; st.ch[h].nch = 8; st.ch[h].c0 = (uint16_t)(16 * j + 8 * h); st.ch[h].zacc = 1; }
         st.n_use = 1;
-        st.use[0].conv = 1; st.use[0].tapmask = TAPS_ALL9; st.use[0].first = j == 0; st.use[0].wtile = (uint32_t)(j * 9);
+        st.use[0].conv = (uint8_t)cd; st.use[0].tapmask = TAPS_ALL9; st.use[0].first = j == 0; st.use[0].wtile = (uint32_t)(j * 9);
     }
     // (2) camera coordinates (3 channels + a zero chunk) -> conv_depth
     {
@@ -1128,16 +1286,22 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
         else st.ch[0].kind = CK_COORDS;
         st.ch[1].kind = CK_NONE;
         st.n_use = 1;
-        st.use[0].conv = 1; st.use[0].tapmask = TAPS_ALL9; st.use[0].first = 0; st.use[0].wtile = (uint32_t)((C_d / 16) * 9);
+        st.use[0].conv = (uint8_t)cd; st.use[0].tapmask = TAPS_ALL9; st.use[0].first = 0; st.use[0].wtile = (uint32_t)((C_d / 16) * 9);
         ++s;
     }
     // (3) image chunks -> conv_image (9 taps) and conv_fused (centre tap)
     for (int j = 0; j < C_i / 16; ++j, ++s) {
         V2Stage& st = q.stage[s];
-        for (int h = 0; h < 2; ++h) { st.ch[h].kind = CK_TMA; st.ch[h].tmap = 0; st.ch[h].nch = 8; st.ch[h].c0 = (uint16_t)(16 * j + 8 * h); }
-        st.n_use = 2;
-        st.use[0].conv = 0; st.use[0].tapmask = TAPS_ALL9; st.use[0].first = j == 0; st.use[0].wtile = (uint32_t)(j * 9);
-        st.use[1].conv = 2; st.use[1].tapmask = TAPS_CENTER; st.use[1].first = j == 0; st.use[1].wtile = (uint32_t)j;
+        for (int h = 0; h < 2; ++h) {
+            V2Chunk& ch = st.ch[h];
+            ch.nch = 8; ch.c0 = (uint16_t)(16 * j + 8 * h);
+            if (skip_image) { ch.kind = image_of ? CK_OF_P0 : CK_TMA_P0; ch.tmap = image_of ? 4 : 0; ch.cls = image_of ? 0 : 1; }
+            else { ch.kind = image_of ? CK_OF : CK_TMA; ch.tmap = image_of ? 4 : 0; }
+        }
+        int u = 0;
+        if (!skip_image) { st.use[u].conv = (uint8_t)ci; st.use[u].tapmask = TAPS_ALL9; st.use[u].first = j == 0; st.use[u].wtile = (uint32_t)(j * 9); ++u; }
+        st.use[u].conv = (uint8_t)cf; st.use[u].tapmask = TAPS_CENTER; st.use[u].first = j == 0; st.use[u].wtile = (uint32_t)j; ++u;
+        st.n_use = u;
     }
     // (4) xyz = coordinates * z, then the incoming fused features -> conv_fused (even pixels only)
     {
@@ -1151,18 +1315,19 @@ int kb_fused_launch(const float* image, long long image_sn, const float* depth, 
                     if (coordinates) { ch.kind = CK_XYZ_T; ch.tmap = 3; ch.nch = 3; ch.c0 = 0; }
                     else ch.kind = CK_XYZ;
                 } else if (k < n_rest) {
-                    ch.kind = CK_TMA_P0; ch.tmap = 2; ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1)); ch.cls = 1;
+                    if (fused_of) { ch.kind = CK_OF_P0; ch.tmap = (uint8_t)(image_of ? 6 : 4); ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1)); ch.cls = 1; }
+                    else { ch.kind = CK_TMA_P0; ch.tmap = 2; ch.nch = 8; ch.c0 = (uint16_t)(8 * (k - 1)); ch.cls = 1; }
                 } else {
                     ch.kind = CK_NONE;
                 }
             }
             st.n_use = 1;
-            st.use[0].conv = 2; st.use[0].tapmask = TAPS_CENTER; st.use[0].first = 0; st.use[0].wtile = (uint32_t)(C_i / 16 + g / 2);
+            st.use[0].conv = (uint8_t)cf; st.use[0].tapmask = TAPS_CENTER; st.use[0].first = 0; st.use[0].wtile = (uint32_t)(C_i / 16 + g / 2);
         }
     }
     KB_CHECK_ARG(s <= V2_MAX_STAGES, "kb(v2): too many stages");
     q.n_stages = s;
-    return v2_launch(q, srcs, V2_MAX_MAPS, map_cls, false, stream);
+    return v2_launch(q, srcs, 4, map_cls, false, stream, n_of ? ofs : nullptr, n_of);
 }
 
 // ---- nearest-2x upsample + 3x3 convolution as four 2x2 convolutions at the SOURCE resolution ---------------------------------

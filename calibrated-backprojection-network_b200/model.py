@@ -11,11 +11,21 @@ as 9 floats per sample instead of an [N,3,H,W] coordinates tensor; skip concaten
 import torch
 
 from . import ops
-from .modules import (CalibratedBackprojectionBlock, ConvBlockWeight, ConvWeight, SparseToDensePool, activation_slope)
+import os
+
+from .modules import (CalibratedBackprojectionBlock, ConvBlockWeight, ConvWeight, OperandFormat, SparseToDensePool, activation_slope)
 
 # Backend of the convolutions that are NOT on the north-star hot path (conv0_*, conv5_*, decoder):
 #   'kbnet' -> this library's fused conv (kbnet_conv2d_forward);  'torch' -> stock cuDNN (the incumbent, for A/B runs).
 CONV_BACKEND = 'kbnet'
+# Opt-in (KBNET_OPERAND_FORMAT=1): conv_image (conv0_image -> KB blocks, its only consumers, src/networks.py:364-475) and the even
+# pixels of conv_fused travel between the blocks in operand format -- bf16 hi/lo 16-byte entries the next block's TMA drops
+# straight into its MMA operand planes (no fp32 staging, no converter pass).  Parity-green (tests/test_operand_format_gpu.py) but
+# MEASURED SLOWER than the fp32 path on B200 (KB block 2: 222 vs 196 us, profiles/r02b_kb_microbench.txt): an operand stage can only
+# be requested once its slot is free, so the load latency the raw ring hides sits on the critical path.  Default off.
+OPERAND_FORMAT = os.environ.get('KBNET_OPERAND_FORMAT', '0') != '0'
+# calibrated_backprojection4's conv_image (3x3 stride 2, 192 -> 384) is dead in KBNetEncoder.forward (src/networks.py:476-523)
+SKIP_DEAD_CONV_IMAGE = os.environ.get('KBNET_SKIP_DEAD_CONV_IMAGE', '1') != '0'
 
 
 def _conv(sources, weight, stride, slope, out=None):
@@ -97,22 +107,46 @@ class KBNetEncoder(torch.nn.Module):
         dev = image.device
         h1, w1 = (h0 - 1) // 2 + 1, (w0 - 1) // 2 + 1
         kinv0, kinv1 = self.inverse_intrinsics(intrinsics, h0, w0, h1, w1)
-        conv_image = _conv([image], self.conv0_image.weight, 1, slope)                   # src/networks.py:364
-        conv_depth = _conv([depth], self.conv0_depth.weight, 1, slope)                   # :365
-        conv_fused = None
-        skips = []
-        h, w = h0, w0
+        blocks = [getattr(self, 'calibrated_backprojection%d' % (lvl + 1)) for lvl in range(4)]
+        # which blocks take / hand on conv_image in operand format (level sizes: h >> lvl)
+        sizes = [(h0, w0)]
         for lvl in range(4):
-            blk = getattr(self, 'calibrated_backprojection%d' % (lvl + 1))
-            ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            sizes.append(((sizes[-1][0] - 1) // 2 + 1, (sizes[-1][1] - 1) // 2 + 1))
+        of_ok = [False] * 5
+        of_ok[:4] = [OPERAND_FORMAT and CONV_BACKEND == 'kbnet' and blk.operand_format_supported(*sizes[lvl]) and blk.n_filter_image % 8 == 0
+                 for lvl, blk in enumerate(blocks)]
+        w0i = self.conv0_image.weight
+        if of_ok[0] and w0i.shape[0] % 8 == 0 and ops.conv3x3_small_takes(w0i.shape[1], w0i.shape[0], 3, 1, slope):
+            conv_image = ops.conv2d_fused([image], w0i, 1, slope, out_of=OperandFormat(n, w0i.shape[0], h0, w0, dev))
+        else:
+            conv_image = _conv([image], w0i, 1, slope)                                   # src/networks.py:364
+            of_ok[0] = False
+        conv_depth = _conv([depth], self.conv0_depth.weight, 1, slope)                   # :365
+        conv_fused = fused_of = None
+        skips = []
+        for lvl, blk in enumerate(blocks):
+            ho, wo = sizes[lvl + 1]
             f_f, f_d = blk.n_filter_fused, blk.n_filter_depth
             skip = torch.empty((n, f_f + f_d, ho, wo), dtype=torch.float32, device=dev)   # cat([fused, depth]) in place
+            # conv_image leaves in operand format when this block runs the fused program and the next block reads it that way;
+            # the last block's conv_image has no consumer (src/networks.py:476-523 only read its shape; conv5_image is fed from
+            # conv4_fused), so it is not computed: the output is identical (SKIP_DEAD_CONV_IMAGE = False computes it anyway)
+            out_image = None
+            need_image = not (lvl == 3 and SKIP_DEAD_CONV_IMAGE and CONV_BACKEND == 'kbnet')
+            if need_image and of_ok[lvl] and of_ok[lvl + 1]:
+                out_image = OperandFormat(n, blk.n_filter_image, ho, wo, dev)
+            # conv_fused goes to the skip buffer as NCHW fp32 (the decoder reads it) and, for the next block -- which reads it at
+            # even pixels only --, additionally as its even pixels in operand format (a quarter of its size)
+            out_fused_of = OperandFormat(n, f_f, ho, wo, dev, even_only=True) if (of_ok[lvl] and of_ok[lvl + 1] and f_f % 8 == 0) else None
             conv_image, conv_depth, conv_fused = blk(image=conv_image, depth=conv_depth,
-                                                     coordinates=kinv0 if lvl == 0 else kinv1, fused=conv_fused,
-                                                     out_fused=skip[:, :f_f], out_depth=skip[:, f_f:])
+                                                     coordinates=kinv0 if lvl == 0 else kinv1,
+                                                     fused=conv_fused if fused_of is None else None, fused_of=fused_of,
+                                                     out_image=out_image, out_fused=skip[:, :f_f], out_depth=skip[:, f_f:],
+                                                     out_fused_of=out_fused_of, need_image=need_image)
+            fused_of = out_fused_of
             skips.append(skip)
-            h, w = ho, wo
-        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        ho, wo = sizes[4][0], sizes[4][1]
+        ho, wo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         f5i, f5d = self.conv5_image.weight.shape[0], self.conv5_depth.weight.shape[0]
         latent = torch.empty((n, f5i + f5d, ho, wo), dtype=torch.float32, device=dev)
         _conv([conv_fused], self.conv5_image.weight, 2, slope, out=latent[:, :f5i])      # :520-523 (input = conv4_fused)

@@ -189,6 +189,49 @@ def invalidate_packs(module):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# operand format: activations stored the way the tensor-core engine consumes them (include/kbnet_b200.h)
+# ---------------------------------------------------------------------------------------------------------
+class OperandFormat(object):
+    """An [N, C, H, W] activation held as two bf16 tensors [N, C/8, 4, H/2, W/2, 8] -- the hi and the lo half of every fp32 value
+    (x ~= hi + lo, 16 mantissa bits), 8 consecutive channels of a pixel in one 16-byte entry, pixels split into the four parity
+    planes (y & 1) * 2 + (x & 1) that a stride-2 convolution reads with unit stride.  ``even_only=True`` keeps plane 0 (the
+    even pixels) only: [N, C/8, 1, H/2, W/2, 8].  Written by the producing kernel's epilogue and loaded by the next KB block with
+    TMA straight into its MMA operand planes.  Exists only between this library's own layers; ``to_nchw()`` gives the fp32
+    tensor back (exact for the bits the engine uses)."""
+
+    def __init__(self, n, c, h, w, device, even_only=False):
+        if c % 8 or h % 2 or w % 2:
+            raise RuntimeError('kbnet_b200: operand format needs a multiple of 8 channels and even H, W (got %d, %d x %d)' % (c, h, w))
+        self.shape = (n, c, h, w)
+        self.even_only = bool(even_only)
+        self.hi = torch.empty((n, c // 8, 1 if even_only else 4, h // 2, w // 2, 8), dtype=torch.bfloat16, device=device)
+        self.lo = torch.empty_like(self.hi)
+        self.device = self.hi.device
+
+    @classmethod
+    def from_nchw(cls, x, even_only=False):
+        x, sn = _view4('x', x)
+        n, c, h, w = x.shape
+        of = cls(n, c, h, w, x.device, even_only)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().kbnet_to_operand_format(x.data_ptr(), sn, n, c, h, w, of.hi.data_ptr(), of.lo.data_ptr(), int(of.even_only),
+                                                     _stream(x.device))
+        _lib.check(rc, 'kbnet_to_operand_format')
+        return of
+
+    def to_nchw(self):
+        if self.even_only:
+            raise RuntimeError('kbnet_b200: an even-pixel operand-format tensor holds a quarter of the pixels; no NCHW form')
+        n, c, h, w = self.shape
+        x = torch.empty((n, c, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().kbnet_from_operand_format(self.hi.data_ptr(), self.lo.data_ptr(), n, c, h, w, x.data_ptr(), c * h * w,
+                                                       _stream(self.device))
+        _lib.check(rc, 'kbnet_from_operand_format')
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------------
 # SparseToDensePool
 # ---------------------------------------------------------------------------------------------------------
 class SparseToDensePool(torch.nn.Module):
@@ -294,16 +337,47 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
         # n_convolution_fused is ignored by the reference too (src/net_utils.py:1335-1341)
         self.conv_fused = ConvWeight(in_channels_fused + 3, n_filter_fused, 1, 2, weight_initializer)
 
-    def forward(self, image, depth, coordinates, fused=None, out_image=None, out_depth=None, out_fused=None):
-        image, image_sn = _view4('image', image)
+    def operand_format_supported(self, h, w, c_f=None):
+        """True when a block input of spatial size (h, w) runs as the fused one-launch program in the tensor-core mode, i.e.
+        ``image`` / ``out_image`` / ``fused_of`` / ``out_fused_of`` may be OperandFormat tensors."""
+        c_f = self.in_channels_fused - self.in_channels_image if c_f is None else c_f
+        return _PRECISION == 'bf16x3' and bool(_lib.load().kbnet_kb_operand_format_supported(
+            self.in_channels_image, self.in_channels_depth, c_f, h, w, self.n_filter_image, self.n_filter_depth, self.n_filter_fused))
+
+    def forward(self, image, depth, coordinates, fused=None, out_image=None, out_depth=None, out_fused=None, fused_of=None,
+                out_fused_of=None, need_image=True):
+        """The reference's ``forward(image, depth, coordinates, fused=None)`` (src/net_utils.py:1343-1371).  Extras used by
+        KBNetEncoder here: ``out_*`` preallocated outputs (channel slices of the skip buffers); ``image`` and ``out_image`` may
+        be OperandFormat tensors (then conv_image is returned as that OperandFormat and no NCHW copy of it is written);
+        ``fused_of`` = `fused` as an even-pixel OperandFormat (`fused` itself may then be None); ``out_fused_of`` = an even-pixel
+        OperandFormat that receives the even pixels of conv_fused in addition to the fp32 output; ``need_image=False`` does not compute conv_image at all (returned
+        as None) -- for a caller that, like KBNetEncoder for its last block (src/networks.py:476-523), never reads it."""
+        image_of = image if isinstance(image, OperandFormat) else None
+        out_image_of = out_image if isinstance(out_image, OperandFormat) else None
+        if out_image_of is not None:
+            out_image = None
         depth, depth_sn = _view4('depth', depth)
-        n, c_i, h, w = image.shape
+        if image_of is not None:
+            if image_of.even_only:
+                raise RuntimeError('kbnet_b200: image needs the full (four-plane) operand format')
+            n, c_i, h, w = image_of.shape
+            image, image_sn = None, c_i * h * w
+            if image_of.device != depth.device:
+                raise RuntimeError('kbnet_b200: image (operand format) on %s but depth on %s' % (image_of.device, depth.device))
+        else:
+            image, image_sn = _view4('image', image)
+            n, c_i, h, w = image.shape
         c_d = depth.shape[1]
-        dev = image.device
+        dev = depth.device
         if depth.shape[0] != n or tuple(depth.shape[-2:]) != (h, w):
-            raise RuntimeError('kbnet_b200: depth shape %s does not match image %s' % (tuple(depth.shape), tuple(image.shape)))
+            raise RuntimeError('kbnet_b200: depth shape %s does not match image %s' % (tuple(depth.shape), (n, c_i, h, w)))
         c_f, fused_sn = 0, 0
-        if fused is not None:
+        if fused_of is not None:
+            if tuple(fused_of.shape[0:1] + fused_of.shape[2:]) != (n, h, w) or fused_of.device != dev or not fused_of.even_only:
+                raise RuntimeError('kbnet_b200: fused (operand format) shape %s does not match image' % (tuple(fused_of.shape),))
+            c_f = fused_of.shape[1]
+            fused = None
+        elif fused is not None:
             fused, fused_sn = _view4('fused', fused)
             c_f = fused.shape[1]
             if fused.shape[0] != n or tuple(fused.shape[-2:]) != (h, w):
@@ -335,8 +409,20 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
                 raise RuntimeError('kbnet_b200: preallocated output must be a [N,%d,%d,%d] float32 channel slice' % (f, ho, wo))
             return t
 
-        o_i, o_d, o_f = _out(out_image, f_i), _out(out_depth, f_d), _out(out_fused, f_f)
+        o_i = _out(out_image, f_i) if (out_image_of is None and need_image) else None
+        o_d, o_f = _out(out_depth, f_d), _out(out_fused, f_f)
         lib = _lib.load()
+        of = None
+        if image_of is not None or out_image_of is not None or fused_of is not None or out_fused_of is not None:
+            for t, f, even in ((out_image_of, f_i, False), (out_fused_of, f_f, True)):
+                if t is not None and (tuple(t.shape) != (n, f, ho, wo) or t.device != dev or t.even_only != even):
+                    raise RuntimeError('kbnet_b200: operand-format output must be [N,%d,%d,%d] on %s (conv_image: full, conv_fused: '
+                                       'even pixels only)' % (f, ho, wo, dev))
+            of = _lib.KBNetKbOperandFormat()
+            for name, t in (('image', image_of), ('fused', fused_of), ('out_image', out_image_of), ('out_fused', out_fused_of)):
+                if t is not None:
+                    setattr(of, name + '_hi', t.hi.data_ptr())
+                    setattr(of, name + '_lo', t.lo.data_ptr())
         ws_bytes = lib.kbnet_kb_workspace_bytes(n, c_i, c_d, c_f, h, w, f_i, f_d, f_f)
         # scratch for the un-fused path (z at even pixels); kept on the module and re-used: no allocation per call
         ws = self.__dict__.get('_kbnet_ws')
@@ -351,14 +437,14 @@ class CalibratedBackprojectionBlock(torch.nn.Module):
         pk_f = packed_weight(self.conv_fused.weight, [c_i, 3, c_f] if c_f else [c_i, 3])
         ptr = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(dev):
-            rc = lib.kbnet_kb_forward(image.data_ptr(), image_sn, depth.data_ptr(), depth_sn,
-                                      fused.data_ptr() if fused is not None else None, fused_sn, coords_ptr, kinv_ptr, n, c_i, c_d, c_f, h, w,
-                                      wi.data_ptr(), f_i, wd.data_ptr(), f_d, wp.data_ptr(), wf.data_ptr(), f_f,
-                                      ptr(pk_i), ptr(pk_d), ptr(pk_f), self.negative_slope,
-                                      o_i.data_ptr(), sn(o_i), o_d.data_ptr(), sn(o_d), o_f.data_ptr(), sn(o_f),
-                                      ws.data_ptr(), ws_bytes, _stream(dev))
+            rc = lib.kbnet_kb_forward_of(ptr(image), image_sn, depth.data_ptr(), depth_sn,
+                                         ptr(fused), fused_sn, coords_ptr, kinv_ptr, n, c_i, c_d, c_f, h, w,
+                                         wi.data_ptr(), f_i, wd.data_ptr(), f_d, wp.data_ptr(), wf.data_ptr(), f_f,
+                                         ptr(pk_i), ptr(pk_d), ptr(pk_f), self.negative_slope,
+                                         ptr(o_i), sn(o_i) if o_i is not None else f_i * ho * wo, o_d.data_ptr(), sn(o_d), o_f.data_ptr(), sn(o_f),
+                                         ws.data_ptr(), ws_bytes, ctypes.byref(of) if of is not None else None, _stream(dev))
         _lib.check(rc, 'kbnet_kb_forward')
-        return o_i, o_d, o_f
+        return (o_i if out_image_of is None else out_image_of), o_d, o_f
 
 
 # ---------------------------------------------------------------------------------------------------------

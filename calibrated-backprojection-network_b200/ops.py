@@ -7,7 +7,7 @@ from . import _lib
 from .modules import _view4, _w, _stream, packed_weight
 
 
-def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
+def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None, out_of=None):
     """out = act(conv_k(cat_c(sources), weight)), padding k//2, no bias.
 
     engine=None picks the kernel by shape: a single full-resolution source with few channels and filters (3x3, stride 1)
@@ -17,6 +17,8 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
     sources: list of 4-D CUDA float32 tensors or ``(tensor, 'up')`` pairs; an ``'up'`` source is nearest-upsampled to
     the spatial size of the first non-upsampled source (or ``size`` given as ``(tensor, 'up', (H, W))``) inside the kernel.
     slope=None means no activation.  ``out`` may be a channel slice of a wider NCHW buffer.
+    ``out_of``: an OperandFormat that receives the result INSTEAD of an NCHW tensor (returned; only the few-channel kernel
+    writes it -- callers check ``conv3x3_small_takes`` first).
     Replaces Conv2d.forward + torch.cat + F.interpolate(mode='nearest') of the reference
     (src/net_utils.py:120-141, 484-499, 1453-1487; src/networks.py:364-365, 520-531).
     """
@@ -47,15 +49,24 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
                            % (ctot, sum(t.shape[1] for t, _, _ in parsed)))
     pad = k // 2
     ho, wo = (h_in + 2 * pad - k) // stride + 1, (w_in + 2 * pad - k) // stride + 1
+    if out_of is not None:
+        if out is not None or tuple(out_of.shape) != (n, f, ho, wo) or out_of.device != dev:
+            raise RuntimeError('kbnet_b200: bad operand-format conv output')
+        if not conv3x3_small_takes(ctot, f, k, stride, slope) or len(parsed) != 1 or parsed[0][2] != 0:
+            raise RuntimeError('kbnet_b200: only the few-channel 3x3 kernel writes operand format')
+        t, sn, _ = parsed[0]
+        with torch.cuda.device(dev):
+            rc = lib.kbnet_conv3x3_small_forward_of(t.data_ptr(), sn, n, ctot, h_in, w_in, w.data_ptr(), f, 0 if slope is None else 1,
+                                                    0.0 if slope is None else float(slope), None, f * ho * wo,
+                                                    out_of.hi.data_ptr(), out_of.lo.data_ptr(), _stream(dev))
+        _lib.check(rc, 'kbnet_conv3x3_small_forward_of')
+        return out_of
     if out is None:
         out = torch.empty((n, f, ho, wo), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (n, f, ho, wo) or out.stride()[1:] != (ho * wo, wo, 1) or out.dtype != torch.float32 or out.device != dev:
         raise RuntimeError('kbnet_b200: bad preallocated conv output')
     osn = out.stride(0) if n > 1 else f * ho * wo
-    from .modules import get_precision
-    if engine is None and len(parsed) == 1 and parsed[0][2] == 0 and get_precision() == 'bf16x3' and \
-            (slope is None or 0.0 <= float(slope) <= 1.0) and lib.kbnet_conv3x3_small_supported(ctot, f, k, stride) and \
-            not (f <= 4 and ctot <= 32):        # <= 4 filters: the exact-fp32 CUDA-core kernel inside kbnet_conv2d_forward
+    if engine is None and len(parsed) == 1 and parsed[0][2] == 0 and conv3x3_small_takes(ctot, f, k, stride, slope):
         t, sn, _ = parsed[0]
         with torch.cuda.device(dev):
             rc = lib.kbnet_conv3x3_small_forward(t.data_ptr(), sn, n, ctot, h_in, w_in, w.data_ptr(), f, 0 if slope is None else 1,
@@ -73,6 +84,14 @@ def conv2d_fused(sources, weight, stride=1, slope=0.2, out=None, engine=None):
                                       out.data_ptr(), osn, _stream(dev))
     _lib.check(rc, 'kbnet_conv2d_forward')
     return out
+
+
+def conv3x3_small_takes(c, f, k, stride, slope):
+    """True when conv2d_fused routes a single full-resolution source of this shape to the few-channel mma.sync kernel."""
+    from .modules import get_precision
+    return get_precision() == 'bf16x3' and (slope is None or 0.0 <= float(slope) <= 1.0) and \
+        bool(_lib.load().kbnet_conv3x3_small_supported(c, f, k, stride)) and \
+        not (f <= 4 and c <= 32)        # <= 4 filters: the exact-fp32 CUDA-core kernel inside kbnet_conv2d_forward
 
 
 def _upconv_packs(weight):

@@ -126,6 +126,58 @@ int kbnet_kb_forward(const float* image, long long image_stride_n,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Operand format -- an OPTIONAL activation layout between this library's own layers (no reference counterpart: the
+ * reference keeps NCHW fp32 between src/networks.py:364 and the KB blocks at :368-475; this is the same data, laid out the
+ * way the tensor-core engine consumes it).  A tensor of C channels (C % 8 == 0, H and W even) is two DEVICE buffers, the bf16
+ * hi half and the bf16 lo half of every fp32 value (x ~= hi + lo, 16 mantissa bits), each
+ *     [N][C/8][4][H/2][W/2] x 16-byte entries,   entry = 8 consecutive channels of one pixel,
+ *     plane index = (y & 1) * 2 + (x & 1), position (y / 2, x / 2)                       ("parity planes")
+ * -- the four pixel sets a stride-2 3x3 convolution reads with unit stride.  The EVEN-PIXEL form keeps plane 0 only,
+ * [N][C/8][H/2][W/2] x 16 B: it is what `fused` needs (the KB block reads it at even pixels only, src/net_utils.py:1360-1369
+ * is a stride-2 1x1 convolution).  Same bytes per value as fp32; 16-byte aligned.  kbnet_operand_format_bytes() = bytes of
+ * ONE half (0 for an unsupported shape).  The fused KB block loads such sources with TMA straight into its MMA operand
+ * planes (no fp32 staging ring, no conversion pass); results equal the fp32-source path (same split of the same values). */
+size_t kbnet_operand_format_bytes(int N, int C, int H, int W, int even_pixels_only);
+int    kbnet_to_operand_format(const float* x, long long x_stride_n, int N, int C, int H, int W, void* of_hi, void* of_lo,
+                               int even_pixels_only, void* stream);
+int    kbnet_from_operand_format(const void* of_hi, const void* of_lo, int N, int C, int H, int W, float* x, long long x_stride_n, void* stream);
+
+/* Optional operand-format side channel of kbnet_kb_forward_of (every member may be NULL = not used):
+ *   image_hi/lo      `image` [N,C_i,H,W] in operand format; the fp32 `image` pointer may then be NULL
+ *   fused_hi/lo      `fused` [N,C_f,H,W] in the EVEN-PIXEL operand format (C_f % 8 == 0); the fp32 `fused` pointer may then be NULL
+ *   out_image_hi/lo  conv_image [N,F_i,Ho,Wo] written in operand format for the next block; `out_image` may then be NULL.
+ *                    With `out_image` NULL and no out_image_hi/lo, conv_image is NOT COMPUTED: KBNetEncoder's last block only
+ *                    reads the shape of its conv_image (src/networks.py:476-523 feed conv5_image from conv4_fused), so the
+ *                    model-level forward drops that convolution; the image is then read at even pixels only.
+ *   out_fused_hi/lo  the even pixels of conv_fused written in the EVEN-PIXEL operand format IN ADDITION to the fp32 `out_fused`
+ *                    (a quarter of its size: what the next block's `fused_hi/lo` wants) */
+typedef struct kbnet_kb_operand_format {
+    const void* image_hi; const void* image_lo;
+    const void* fused_hi; const void* fused_lo;
+    void* out_image_hi; void* out_image_lo;
+    void* out_fused_hi; void* out_fused_lo;
+} kbnet_kb_operand_format;
+
+/* 1 when a KB block of this shape runs as the fused one-launch program, i.e. may use the operand-format side channel. */
+int kbnet_kb_operand_format_supported(int C_i, int C_d, int C_f, int H, int W, int F_i, int F_d, int F_f);
+
+/* kbnet_kb_forward with the operand-format side channel.  `of` == NULL is exactly kbnet_kb_forward.  Operand-format
+ * sources need the fused one-launch program (packed weights given, C_i % 16 == 0, C_d % 16 == 0, W % 4 == 0); any other
+ * configuration returns KBNET_E_BADARG -- convert back with kbnet_from_operand_format and call kbnet_kb_forward. */
+int kbnet_kb_forward_of(const float* image, long long image_stride_n,
+                        const float* depth, long long depth_stride_n,
+                        const float* fused, long long fused_stride_n,
+                        const float* coordinates, const float* kinv,
+                        int N, int C_i, int C_d, int C_f, int H, int W,
+                        const float* w_image, int F_i, const float* w_depth, int F_d,
+                        const float* w_proj, const float* w_fused, int F_f,
+                        const void* wpack_image, const void* wpack_depth, const void* wpack_fused, float neg_slope,
+                        float* out_image, long long out_image_stride_n,
+                        float* out_depth, long long out_depth_stride_n,
+                        float* out_fused, long long out_fused_stride_n,
+                        void* workspace, size_t workspace_bytes, const kbnet_kb_operand_format* of, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Generic fused convolution -- replaces net_utils.Conv2d.forward (src/net_utils.py:120-141) together with the
  * torch.cat / nearest-interpolate that feed it in KBNetEncoder.forward (src/networks.py:364-365,520-531),
  * DecoderBlock.forward / UpConv2d.forward (src/net_utils.py:1453-1487, 484-499).
@@ -180,6 +232,10 @@ int kbnet_conv3x3_depth_head_forward(const float* x, long long x_stride_n, int N
 int kbnet_conv3x3_small_supported(int C, int F, int ksize, int stride);
 int kbnet_conv3x3_small_forward(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
                                 float neg_slope, float* y, long long y_stride_n, void* stream);
+/* ... the same with an operand-format copy of the result (F % 8 == 0) for a following KB block; `y` may be NULL when only that
+ * copy is wanted (conv0_image feeds calibrated_backprojection1 only, src/networks.py:364-373). */
+int kbnet_conv3x3_small_forward_of(const float* x, long long x_stride_n, int N, int C, int H, int W, const float* w, int F, int act,
+                                   float neg_slope, float* y, long long y_stride_n, void* of_hi, void* of_lo, void* stream);
 
 /* Element-wise half of the reference's on-disk depth format -- a 16-bit PNG holding depth * 256 (src/data_utils.py:88-167;
  * the PNG container itself is host work, kbnet_b200/io.py).
