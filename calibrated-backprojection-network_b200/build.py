@@ -29,7 +29,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    extra = ['-DKBNET_V2_STAMPS'] if os.environ.get('KBNET_V2_STAMPS') else []   # role timelines (tools/v2_timeline.py)
+    extra = (['-DKBNET_V2_STAMPS'] if os.environ.get('KBNET_V2_STAMPS') else []) + ['-D' + f for f in os.environ.get('KBNET_V2_DEFS', '').split() if f]   # role timelines (tools/v2_timeline.py)
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:

@@ -185,6 +185,29 @@ struct Ring {
     } while (0)
 #endif
 
+// wait flavours of the roles (see umma.cuh).  Measured on B200 (KB block 2, 196 us with plain spinning everywhere): backing off in
+// the producers / epilogue or polling with one lane per converter warp all made the block SLOWER (324 us with all three) -- every
+// role is on some latency chain -- so plain spinning is the default; the variants stay selectable at compile time.
+#ifdef KBNET_V2_WAIT_CONV1
+#define V2_WAIT_CONV(bar, par) mbar_wait_warp(bar, par, lane)
+#else
+#define V2_WAIT_CONV(bar, par) mbar_wait(bar, par)
+#endif
+#ifdef KBNET_V2_WAIT_PROD
+#define V2_WAIT_RELAXED(bar, par, ns) mbar_wait_relaxed(bar, par, ns)
+#else
+#define V2_WAIT_RELAXED(bar, par, ns) mbar_wait(bar, par)
+#endif
+#ifdef KBNET_V2_WAIT_EPI
+#define V2_WAIT_EPI(bar, par)                      \
+    do {                                           \
+        if (lane == 0) mbar_wait_relaxed(bar, par, 128); \
+        __syncwarp();                              \
+    } while (0)
+#else
+#define V2_WAIT_EPI(bar, par) mbar_wait(bar, par)
+#endif
+
 struct TileCoord {
     int n, oy0, ox0, split;
 };
@@ -271,7 +294,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
             for (int s = 0; s < p.n_stages; ++s) {
                 const V2Stage& st = p.stage[s];
                 const int aslot = (int)a_r.slot;
-                mbar_wait(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
+                V2_WAIT_CONV(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
                 if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
                 uint8_t* A = sA + (size_t)aslot * p.a_bytes;
 #pragma unroll 1
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                     int rslot = 0;
                     if (is_tma) {
                         rslot = (int)raw_r.slot;
-                        mbar_wait(BAR(B_RAW_FULL + rslot), raw_r.phase);
+                        V2_WAIT_CONV(BAR(B_RAW_FULL + rslot), raw_r.phase);
                         if (dbg_on) { V2_STAMP(0, dbg_i); ++dbg_i; }
                         raw = reinterpret_cast<const float*>(sRaw + (size_t)rslot * p.raw_bytes);
                     }
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                         const V2Chunk ch = p.stage[s].ch[h];
                         if (ch.kind == CK_TMA || ch.kind == CK_TMA_P0 || ch.kind == CK_XYZ_T) {
                             const int rslot = (int)raw_r.slot;
-                            mbar_wait(BAR(B_RAW_EMPTY + rslot), raw_r.phase ^ 1u);
+                            V2_WAIT_RELAXED(BAR(B_RAW_EMPTY + rslot), raw_r.phase ^ 1u, 64);
                             V2_STAMP(1, dbg_i); ++dbg_i;
                             mbar_arrive_expect_tx(BAR(B_RAW_FULL + rslot), ch.cls ? bytes1 : bytes0);
                             tma_load_4d(smem_u32(sRaw + (size_t)rslot * p.raw_bytes), &maps.m[ch.tmap], ch.cls ? x1c : x0c, ch.cls ? y1c : y0c,
@@ -463,7 +486,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                         for (int t0 = 0; t0 < ntap; t0 += Tu, w_r.advance((uint32_t)p.n_w)) {
                             const int nt = ntap - t0 < Tu ? ntap - t0 : Tu;
                             const int ws = (int)w_r.slot;
-                            mbar_wait(BAR(B_W_EMPTY + ws), w_r.phase ^ 1u);
+                            V2_WAIT_RELAXED(BAR(B_W_EMPTY + ws), w_r.phase ^ 1u, 32);
                             const uint8_t* src = cv.wpack + (size_t)(us.wtile + t0) * tile_b + (size_t)split * piece;
                             const uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
                             mbar_arrive_expect_tx(BAR(B_W_FULL + ws), (uint32_t)nt * piece);
@@ -494,7 +517,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                 for (int s = 0; s < p.n_stages; ++s) {
                     const V2Stage& st = p.stage[s];
                     const int aslot = (int)a_r.slot;
-                    mbar_wait(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u);
+                    V2_WAIT_RELAXED(BAR(B_A_EMPTY + aslot), a_r.phase ^ 1u, 32);
                     uint32_t nbox = 0;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) nbox += st.ch[h].kind == CK_OF ? 8u : (st.ch[h].kind == CK_OF_P0 ? 2u : 0u);
@@ -612,7 +635,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
         for (long long tile = tile0; tile < p.n_tiles; tile += tstep) {
             const TileCoord tc = decode_tile(p, tile);
             const uint32_t buf = t_r.slot;
-            mbar_wait(BAR(B_ACC_FULL + buf), t_r.phase);
+            V2_WAIT_EPI(BAR(B_ACC_FULL + buf), t_r.phase);
             if (tid == 12 * 32) { V2_STAMP(3, dbg_i); ++dbg_i; }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * tile_cols + ((uint32_t)(quarter * 32) << 16);

@@ -343,13 +343,25 @@ __device__ __forceinline__ void hwindow_ct(const float* __restrict__ src, float 
         const float4 t = *reinterpret_cast<const float4*>(src + LO + 4 * q);
         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
+    auto op = [](float a, float b) { return IS_MIN ? min_nan(a, b) : max_nan(a, b); };
+    if (RK >= 2 && LH == 4) {
+        // The four windows [C + i - RK, C + i + RK] share the core [C + 3 - RK, C + RK] (2 RK - 2 elements): RK + 5 three-input
+        // min / max instructions per strip instead of 4 RK.  min / max are exact, commutative, associative and NaN-propagating
+        // here, so the regrouping is bit-exact.
+        float core = v[C + 3 - RK];
 #pragma unroll
-    for (int i = 0; i < LH; ++i) m[i] = v[C + i];
+        for (int e = C + 4 - RK; e <= C + RK; e += 2) core = e + 1 <= C + RK ? op(core, op(v[e], v[e + 1])) : op(core, v[e]);
+        const float L0 = v[C - RK], L1 = v[C - RK + 1], L2 = v[C - RK + 2], R1 = v[C + RK + 1], R2 = v[C + RK + 2], R3 = v[C + RK + 3];
+        const float a = op(core, op(L1, L2)), b = op(core, op(R1, R2));
+        m[0] = op(a, L0); m[1] = op(a, R1); m[2] = op(b, L2); m[3] = op(b, R3);
+    } else {
 #pragma unroll
-    for (int r = 1; r <= RK; ++r) {
+        for (int i = 0; i < LH; ++i) m[i] = v[C + i];
 #pragma unroll
-        for (int i = 0; i < LH; ++i)
-            m[i] = IS_MIN ? min_nan(m[i], min_nan(v[C + i - r], v[C + i + r])) : max_nan(m[i], max_nan(v[C + i - r], v[C + i + r]));
+        for (int r = 1; r <= RK; ++r) {
+#pragma unroll
+            for (int i = 0; i < LH; ++i) m[i] = op(m[i], op(v[C + i - r], v[C + i + r]));
+        }
     }
 }
 

@@ -40,6 +40,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+// Wait of a role that is NOT on the critical path (producers running ahead, the epilogue): back off between polls.  A failed
+// try_wait returns after a few dozen clocks, so a dozen spinning warps keep the SM's barrier / shared-memory pipe busy and stretch
+// the polls of the warps that ARE on the critical path (the MMA issuer's waits took 230-290 clk even on completed phases,
+// profiles/r02b_kb_timeline.txt).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(ns);
+    }
+    __trap();
+}
+// One lane polls for the whole warp (1/32 of the barrier traffic); __syncwarp() hands the acquired state to the other lanes.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
