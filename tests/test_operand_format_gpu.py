@@ -176,8 +176,9 @@ def test_model_with_and_without_operand_format():
             M.OPERAND_FORMAT, M.SKIP_DEAD_CONV_IMAGE = of0, skip0
     base = outs[(False, False)]
     assert len(set(launches.values())) == 1, 'operand format must not add launches: %r' % (launches,)
-    assert torch.equal(outs[(False, True)], base), 'dropping the dead conv_image of block 4 must not change the output'
-    assert torch.equal(outs[(True, True)], outs[(True, False)])
+    # (not bit-equal in general: the program without conv_image may get another tile plan, e.g. the dual-N split mode)
+    assert_close(outs[(False, True)], base, tol=2e-5, what='dropping the dead conv_image of block 4 must not change the output')
+    assert_close(outs[(True, True)], outs[(True, False)], tol=2e-5, what='... nor in operand-format mode')
     assert_close(outs[(True, True)], base, tol=2e-5, what='model operand format vs NCHW')
     assert_close(outs[(True, True)], ref, what='model operand format vs oracle')
     assert_close(base, ref, what='model NCHW vs oracle')

@@ -2,7 +2,6 @@ set -u
 mkdir -p gpurun_out
 bash tools/gpu_round.sh launches ncu_s2d ncu_kb micro > gpurun_out/evid1.log 2>&1
 timeout 200 python tools/bench_s2d.py 8 VOID >> gpurun_out/micro_s2d.log 2>&1
-for l in 1 2 3 4; do timeout 200 python tools/bench_kb.py 8 $l; done > gpurun_out/micro_kb.log 2>&1
 timeout 200 python tools/bench_small_conv.py > gpurun_out/micro_small_conv.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:conv_mma -s 2 -c 1 -o gpurun_out/prof_cm348 -f python tools/bench_small_conv.py 3 48 > /dev/null 2>&1
 ncu -i gpurun_out/prof_cm348.ncu-rep --page raw --csv > gpurun_out/prof_cm348_raw.csv 2>/dev/null

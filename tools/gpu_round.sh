@@ -34,7 +34,7 @@ sanitize)
   done;;
 micro)
   timeout 300 python tools/bench_s2d.py > gpurun_out/micro_s2d.log 2>&1; cat gpurun_out/micro_s2d.log
-  timeout 300 python tools/bench_kb.py all > gpurun_out/micro_kb.log 2>&1; cat gpurun_out/micro_kb.log;;
+  timeout 300 python tools/bench_kb.py > gpurun_out/micro_kb.log 2>&1; cat gpurun_out/micro_kb.log;;
 layers)
   timeout 300 python tools/profile_layers.py > gpurun_out/layers.log 2>&1; cat gpurun_out/layers.log;;
 probe)
@@ -47,7 +47,7 @@ ncu_s2d)
   ncu -i gpurun_out/prof_s2d.ncu-rep --page source --csv > gpurun_out/prof_s2d_source.csv 2>/dev/null;;
 ncu_kb)
   # the fused KB block on BASELINE config 2 (tools/bench_kb.py launches nothing else from the tensor-core engine)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_v2 -s 6 -c 1 -o gpurun_out/prof_kb2 -f python tools/bench_kb.py > gpurun_out/ncu_kb.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_v2 -s 6 -c 1 -o gpurun_out/prof_kb2 -f env KBNET_AUTOTUNE=0 KBNET_V2_PLAN=2,62,1,0 python tools/bench_kb.py 8 2 nchw > gpurun_out/ncu_kb.log 2>&1
   ncu -i gpurun_out/prof_kb2.ncu-rep --page raw --csv > gpurun_out/prof_kb2_raw.csv 2>/dev/null;;
 esac
 done
