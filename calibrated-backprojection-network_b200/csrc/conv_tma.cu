@@ -23,7 +23,18 @@
 // (free below N ~ 48, profiles/r01_umma_probe.md) and the epilogue adds the two column groups ("dual" mode).
 //
 // Roles (512 threads): warps 0-7 converters | warp 8 activation TMA | warp 9 weight TMA | warp 10 MMA issuer + TMEM
-// allocator | warps 12-15 epilogue (TMEM lane quarter = warp % 4).  (warp counts: conv_warps(), cta_threads())
+// allocator | warp 11 operand-format TMA (sources already stored as bf16 hi/lo operand planes, operand_format.cu) |
+// warps 12-15 epilogue (TMEM lane quarter = warp % 4).  (warp counts: conv_warps(), cta_threads())
+// The MMA issuer walks a command table the host flattens from the program for the chosen tile plan (build_commands).
+//
+// What bounds the low-N / low-K programs (KB blocks, measured on B200, profiles/r02b_kb_knockout.txt): not one role but the
+// hand-over skeleton.  KB block 2 takes 196 us; with the MMAs compiled out 158 us, with the conversion compiled out 171 us,
+// with the epilogue stores compiled out 190 us, and with ALL THREE compiled out (only TMA loads, weight streaming and mbarrier
+// hand-overs left) still 117 us: every tile of 124 output pixels streams 240 KB of packed weights through a 2 x 24 KB ring
+// (22 refills of ~1.2 k clk latency, two in flight) and crosses 9 operand stages of a 2-deep ring, each hand-over costing a
+// ~250 clk mbarrier hop.  Shared memory (227 KB) leaves no room for deeper rings at this tile size, TMEM (3 accumulators = 224
+// columns) none for a second M-block per tile.  Compile-time switches for these experiments: KBNET_V2_KO_MMA / _KO_CONV / _KO_EPI
+// (results are garbage with them), KBNET_V2_WAIT_* (wait flavours), KBNET_V2_STAMPS (role timelines).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -303,6 +314,16 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                     const int kind = ch.kind;
                     if (kind == CK_OF || kind == CK_OF_P0) continue;   // lands in the operand planes by TMA (warp CW + 3)
                     const bool is_tma = kind == CK_TMA || kind == CK_TMA_P0 || kind == CK_XYZ_T;
+#ifdef KBNET_V2_KO_CONV
+                    if (is_tma) {
+                        const int rs = (int)raw_r.slot;
+                        V2_WAIT_CONV(BAR(B_RAW_FULL + rs), raw_r.phase);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(B_RAW_EMPTY + rs));
+                        raw_r.advance((uint32_t)p.n_raw);
+                    }
+                    continue;
+#endif
                     const float* raw = nullptr;
                     int rslot = 0;
                     if (is_tma) {
@@ -595,6 +616,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                     uint32_t d = acc + (c.y >> 16);
                     const uint32_t idesc = c.z;
                     const uint32_t accum = flags & CMD_ACCUM;
+#ifndef KBNET_V2_KO_MMA   // (knock-out experiments: which role bounds a tile?  results are garbage with these flags)
                     if (DUAL) {  // B' = [b_hi | b_lo] interleaved per 8-filter group: all four hi/lo products in two MMAs
 #pragma unroll 1
                         for (int mb = 0; mb < MB; ++mb, a0 += 128u, d += cols_block) {
@@ -609,6 +631,9 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                             mma_bf16_ss(d, make_desc(a0, desc_hi), make_desc(b16 + 16u, b_desc_hi), idesc, 1u);
                         }
                     }
+#else
+                    (void)a0; (void)b16; (void)d; (void)idesc; (void)accum;
+#endif
                     if (flags & CMD_COMMIT_W) {
                         mma_commit(BAR(B_W_EMPTY + w_r.slot));
                         w_r.advance(n_w);
@@ -680,7 +705,11 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 #pragma unroll
                             for (int k = 0; k < 16; ++k) o[k] = leaky(o[k], p.slope);
                         }
+#ifdef KBNET_V2_KO_EPI
+                        if (valid && cv.out != nullptr && o[0] == 12345.678f) {
+#else
                         if (valid && cv.out != nullptr) {
+#endif
                             float* d = dst;
                             if (c + 16 <= nf) {
 #pragma unroll
