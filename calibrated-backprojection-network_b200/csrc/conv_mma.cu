@@ -90,7 +90,8 @@ __device__ __forceinline__ int entry_of(int row, int c) { return row * QROW + (c
 
 // MODE / NCH: operand packing (see the header);  NTW: n8 filter tiles per warp;  NSPLIT: the two warps of a column block split
 // the FILTERS (each sweeps all 16 rows) instead of the rows (each sweeps 8 rows for all filters)
-template <int MODE, int NCH, int NTW, bool NSPLIT>
+// OF: the instantiation that can write the operand-format copy (its address arithmetic and split stay out of the plain kernel)
+template <int MODE, int NCH, int NTW, bool NSPLIT, bool OF>
 __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__ MmaConvParams p, const __grid_constant__ CUtensorMap tm_x) {
     using G = Geo<MODE, NCH>;
     constexpr int NPL = G::NPL, STEPS = G::STEPS;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__
         for (int j = 0; j < NTW; ++j)
             optr[j] = p.out + (size_t)n * p.out_stride_n + (size_t)(8 * (nt0 + j) + 2 * t) * plane + (size_t)(y0 + row0) * W + gxa;
         const bool full = y0 + TH <= H && x0 + TW <= W && (W & 1) == 0 && ((uintptr_t)p.out & 7) == 0 && (p.out_stride_n & 1) == 0;
-        const bool want_nchw = p.out != nullptr, want_of = p.of_hi != nullptr;
+        const bool want_nchw = !OF || p.out != nullptr, want_of = OF && p.of_hi != nullptr;
         const int of_cg = (F + 7) >> 3;
         // operand-format entry of (chunk, parity plane, y / 2, x / 2): 16 bytes; this lane owns bytes [4t, 4t + 4) of the entries of
         // its two pixels, which sit in the even-column and the odd-column plane of the row's parity (H and W are even)
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__
                     float* d0 = optr[j];
                     float* d1 = d0 + plane;
                     optr[j] += W;
-                    if (want_of && y0 + row0 + li < H && f0 < F) {
+                    if (OF && want_of && y0 + row0 + li < H && f0 < F) {
                         uint32_t h0, l0, h1, l1;
                         split_rn(v0, v1, h0, l0);             // pixel gxa: filters f0, f0 + 1
                         split_rn(v2, v3, h1, l1);             // pixel gxa + 1
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(NT, 2) conv_mma_kernel(const __grid_constant__
                         if (in_a) { *reinterpret_cast<uint32_t*>(p.of_hi + e) = h0; *reinterpret_cast<uint32_t*>(p.of_lo + e) = l0; }
                         if (in_b) { *reinterpret_cast<uint32_t*>(p.of_hi + e + of_plane) = h1; *reinterpret_cast<uint32_t*>(p.of_lo + e + of_plane) = l1; }
                     }
-                    if (!want_nchw) continue;
+                    if (OF && !want_nchw) continue;
                     if (full && f0 + 1 < F) {
                         *reinterpret_cast<float2*>(d0) = make_float2(v0, v2);
                         *reinterpret_cast<float2*>(d1) = make_float2(v1, v3);
@@ -372,7 +373,7 @@ int launch(MmaConvParams& p, cudaStream_t stream) {
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     p.use_tma = make_map(&tm, p) ? 1 : 0;
-    auto kern = conv_mma_kernel<MODE, NCH, NTW, NSPLIT>;
+    auto kern = p.of_hi ? conv_mma_kernel<MODE, NCH, NTW, NSPLIT, true> : conv_mma_kernel<MODE, NCH, NTW, NSPLIT, false>;
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles_x = cdiv(p.W, TW), tiles_y = cdiv(p.H, TH);
     KB_CHECK_ARG(tiles_y <= 65535 && p.N <= 65535, "conv_mma: more than 65535 tile rows or samples in one launch");

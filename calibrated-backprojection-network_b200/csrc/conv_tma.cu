@@ -235,7 +235,9 @@ __device__ __forceinline__ TileCoord decode_tile(const V2Params& p, long long ti
     return t;
 }
 
-template <int GEO, bool DUAL>
+// OF: the instantiation with the operand-format producer role and epilogue copy (stride-2 3x3 programs only); the plain kernels
+// carry none of that code -- their hot loops are sensitive to every KB of instructions (see the header)
+template <int GEO, bool DUAL, bool OF = false>
 __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ V2Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 
     if (tid == 0) {
         for (int i = 0; i < V2_MAX_RAW; ++i) { mbar_init(BAR(B_RAW_FULL + i), 1); mbar_init(BAR(B_RAW_EMPTY + i), CW); }
-        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), CW + (p.has_of ? 1 : 0)); mbar_init(BAR(B_A_EMPTY + i), 1); }
+        for (int i = 0; i < V2_MAX_A; ++i) { mbar_init(BAR(B_A_FULL + i), CW + (OF && p.has_of ? 1 : 0)); mbar_init(BAR(B_A_EMPTY + i), 1); }
         for (int i = 0; i < V2_MAX_W; ++i) { mbar_init(BAR(B_W_FULL + i), 1); mbar_init(BAR(B_W_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACC_FULL + i), 1); mbar_init(BAR(B_ACC_EMPTY + i), 4); }
         fence_mbar_init();
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                 for (int h = 0; h < 2; ++h) {
                     const V2Chunk ch = st.ch[h];
                     const int kind = ch.kind;
-                    if (kind == CK_OF || kind == CK_OF_P0) continue;   // lands in the operand planes by TMA (warp CW + 3)
+                    if (OF && (kind == CK_OF || kind == CK_OF_P0)) continue;   // lands in the operand planes by TMA (warp CW + 3)
                     const bool is_tma = kind == CK_TMA || kind == CK_TMA_P0 || kind == CK_XYZ_T;
 #ifdef KBNET_V2_KO_CONV
                     if (is_tma) {
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
             }
         }
         __syncwarp();
-    } else if (warp == CW + 3) {
+    } else if (OF && warp == CW + 3) {
         // =================================================================================================================
         // operand-format producer (one thread): chunks whose source already holds bf16 hi / lo 16-byte entries are loaded by TMA
         // STRAIGHT into the operand planes of the A stage (a 5-D box with traversal stride 2 in x and y is one parity plane) --
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
 #ifdef KBNET_V2_KO_EPI
                         if (valid && cv.out != nullptr && o[0] == 12345.678f) {
 #else
-                        if (valid && cv.out != nullptr) {
+                        if (valid && (!OF || cv.out != nullptr)) {
 #endif
                             float* d = dst;
                             if (c + 16 <= nf) {
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                             }
                         }
                         // operand-format copy: 8 filters of this pixel = one 16-byte entry (hi) + one (lo) in the pixel's parity plane
-                        if (valid && cv.of_hi != nullptr && !(cv.of_even && ((oy | ox) & 1))) {
+                        if (OF && valid && cv.of_hi != nullptr && !(cv.of_even && ((oy | ox) & 1))) {
                             const size_t of_plane = (size_t)(p.Hout >> 1) * (size_t)(p.Wout >> 1);
                             const size_t pix = (size_t)(oy >> 1) * (size_t)(p.Wout >> 1) + (size_t)(ox >> 1);
 #pragma unroll
@@ -1045,20 +1047,27 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
                 "raw %d x %d B, A %d x %d B, W %d x %d B, smem %lld | tmem %d cols x %d bufs\n",
                 geo, p.N, p.Hin, p.Win, p.Hout, p.Wout, p.n_stages, p.n_convs, p.conv[0].Npad, p.conv[1].Npad, p.conv[2].Npad + p.conv[3].Npad, p.R, p.TW, p.P, p.MB,
                 p.n_split, p.dual, p.T, p.n_tiles, grid, p.n_raw, p.raw_bytes, p.n_a, p.a_bytes, p.n_w, p.w_bytes, used, p.MB * p.cols_block, p.acc_bufs);
-#define V2_LAUNCH(G)                                                                                                          \
-    do {                                                                                                                      \
-        if (p.dual) {                                                                                                         \
-            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));   \
-            conv_v2_kernel<G, true><<<(unsigned)grid, cta_threads(G), (size_t)used, stream>>>(p, maps);                         \
-        } else {                                                                                                              \
-            KB_CUDA(cudaFuncSetAttribute(conv_v2_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));  \
-            conv_v2_kernel<G, false><<<(unsigned)grid, cta_threads(G), (size_t)used, stream>>>(p, maps);                         \
-        }                                                                                                                     \
+#define V2_LAUNCH_K(KERN, G)                                                                                   \
+    do {                                                                                                       \
+        KB_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));           \
+        KERN<<<(unsigned)grid, cta_threads(G), (size_t)used, stream>>>(p, maps);                               \
     } while (0)
+#define V2_LAUNCH(G)                                                      \
+    do {                                                                  \
+        if (p.dual) V2_LAUNCH_K((conv_v2_kernel<G, true, false>), G);     \
+        else        V2_LAUNCH_K((conv_v2_kernel<G, false, false>), G);    \
+    } while (0)
+    bool any_of_out = false;   // an operand-format copy of some output, or operand-format sources: the OF instantiation
+    for (int j = 0; j < p.n_convs; ++j) any_of_out = any_of_out || p.conv[j].of_hi != nullptr || p.conv[j].out == nullptr;
+    if (geo == G_S2K3 && (p.has_of || any_of_out)) {
+        if (p.dual) V2_LAUNCH_K((conv_v2_kernel<G_S2K3, true, true>), G_S2K3);
+        else        V2_LAUNCH_K((conv_v2_kernel<G_S2K3, false, true>), G_S2K3);
+    } else
     if (geo == G_S1K3) V2_LAUNCH(G_S1K3);
     else if (geo == G_S1K1) V2_LAUNCH(G_S1K1);
     else if (geo == G_S2K3) V2_LAUNCH(G_S2K3);
     else V2_LAUNCH(G_S2K1);
+#undef V2_LAUNCH_K
 #undef V2_LAUNCH
     KB_CUDA(cudaGetLastError());
     count_launch();
