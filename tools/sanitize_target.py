@@ -1,5 +1,6 @@
 """One launch of every hot kernel at small sizes, for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
-fused S2D (KITTI and VOID pool sets), fused KB block (K^-1 and coordinates paths), plain conv, up-convolution, output head.
+fused S2D (KITTI and VOID pool sets), fused KB block (K^-1 and coordinates paths, operand-format hand-over, no conv_image),
+plain conv, few-channel conv with operand-format output, up-convolution, output head.
 Run:  compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
 import os
 import sys
@@ -30,6 +31,18 @@ coords = torch.matmul(torch.inverse(k), xy.reshape(1, 3, -1).repeat(2, 1, 1)).vi
 b = kb(img, dep, coords, fus)
 for u, v in zip(a, b):
     assert torch.isfinite(u).all() and (u - v).abs().max() < 1e-3
+# operand-format hand-over (separate kernel instantiations) and the block without conv_image
+from kbnet_b200.modules import OperandFormat  # noqa: E402
+of_i, of_f = OperandFormat(2, 32, 16, 40, dev), OperandFormat(2, 32, 16, 40, dev, even_only=True)
+c = kb(OperandFormat.from_nchw(img), dep, torch.inverse(k).to(dev), None, out_image=of_i,
+       fused_of=OperandFormat.from_nchw(fus, even_only=True), out_fused_of=of_f)
+assert (of_i.to_nchw() - a[0]).abs().max() < 1e-3 and (c[2] - a[2]).abs().max() < 1e-3
+d = kb(img, dep, torch.inverse(k).to(dev), fus, need_image=False)
+assert d[0] is None and (d[1] - a[1]).abs().max() < 1e-3 and (d[2] - a[2]).abs().max() < 1e-3
+wi = torch.randn(48, 3, 3, 3, generator=gen).to(dev) * 0.2
+rgb = torch.rand(2, 3, 32, 80, generator=gen).to(dev)
+of_c = kbnet_b200.ops.conv2d_fused([rgb], wi, 1, 0.2, out_of=OperandFormat(2, 48, 32, 80, dev))
+assert (of_c.to_nchw() - kbnet_b200.ops.conv2d_fused([rgb], wi, 1, 0.2)).abs().max() < 1e-3
 w = torch.randn(32, 48, 3, 3, generator=gen).to(dev) * 0.1
 skip = torch.rand(2, 32, 32, 80, generator=gen).to(dev)
 c1 = kbnet_b200.ops.conv2d_fused([img, skip], w, 1, 0.2)
