@@ -808,10 +808,12 @@ double mma_cycles(int N) {  // measured with a lean single-lane issue loop, tool
 
 struct V2Plan {  // what the tile search decides
     int R, TW, n_split, dual;
+    int wcap;  // bytes of weights per ring slot (0 = the default 24 KB); only the measured selection varies it
+    int ring;  // which ring gets the spare shared memory first: 0 default order, 1 operand stages, 2 weights, 3 raw tiles (measured selection)
 };
 
 // Fill the geometry-dependent fields of p for a candidate (R, TW, n_split); returns the shared-memory footprint or -1.
-long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool has_up) {
+long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool has_up, int plan_wcap = 0) {
     const int geo = p.geo;
     p.R = R; p.TW = TW; p.n_split = n_split; p.dual = dual;
     int max_shift;
@@ -848,8 +850,9 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     p.raw_bytes = roundup(raw0 > raw1 ? raw0 : raw1, 128);
     p.a_bytes = roundup(p.n_planes * 4 * p.plane_px * 16, 128);
     // weight-ring slot: as many taps of a 3x3 use as fit ~24 KB (one barrier round trip and one bulk copy per slot)
-    static const int wcap = getenv("KBNET_V2_WCAP") ? atoi(getenv("KBNET_V2_WCAP")) : 24 * 1024;  // bytes of weights per ring slot (debugging aid)
-    p.T = max_nsl * 64 * 9 <= wcap ? 9 : (max_nsl * 64 * 4 <= wcap ? 4 : (max_nsl * 64 * 3 <= wcap ? 3 : 1));
+    static const int env_wcap = getenv("KBNET_V2_WCAP") ? atoi(getenv("KBNET_V2_WCAP")) : 0;  // debugging aid: overrides the plan
+    const int wcap = env_wcap > 0 ? env_wcap : (plan_wcap > 0 ? plan_wcap : 24 * 1024);      // bytes of weights per ring slot
+    p.T = max_nsl * 64 * 9 <= wcap ? 9 : (max_nsl * 64 * 4 <= wcap ? 4 : (max_nsl * 64 * 3 <= wcap ? 3 : (max_nsl * 64 * 2 <= wcap ? 2 : 1)));
     int max_taps = 1;
     for (int j = 0; j < p.n_convs; ++j) max_taps = p.conv[j].ntaps > max_taps ? p.conv[j].ntaps : max_taps;
     if (p.T > max_taps) p.T = max_taps;
@@ -908,7 +911,7 @@ std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks
                 if (TW == last_tw) continue;
                 last_tw = TW;
                 double best = 1e300;
-                V2Plan plan = {0, 0, 0, 0};
+                V2Plan plan = {0, 0, 0, 0, 0, 0};
                 for (int R = r_step; R <= 64; R += r_step) {
                     if (R - r_step >= p.Hout) break;
                     const long long smem_min = apply_geometry(trial, R, TW, n_split, dual, has_up);
@@ -926,7 +929,7 @@ std::vector<Candidate> search_plans(const V2Params& p, bool has_up, int n_chunks
                     if (trial.acc_bufs == 1) tile += epi;
                     const double waves = (double)cdiv((int)(trial.n_tiles > (1 << 30) ? (1 << 30) : trial.n_tiles), sms);
                     const double total = waves * tile + tile + 4000.0;  // + pipeline fill
-                    if (total < best) { best = total; plan = {R, TW, n_split, dual}; }
+                    if (total < best) { best = total; plan = {R, TW, n_split, dual, 0, 0}; }
                 }
                 if (plan.R > 0) cands.push_back({plan, best});
             }
@@ -994,7 +997,7 @@ struct OfSrc {   // operand-format tensor: hi and lo halves of the bf16 split, `
 int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src, int n_maps, const uint8_t* map_cls, bool has_up, int sms,
                      cudaStream_t stream, bool report, const OfSrc* of_src = nullptr, int n_of = 0) {
     const int geo = p.geo;
-    long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up);
+    long long used = apply_geometry(p, plan.R, plan.TW, plan.n_split, plan.dual, has_up, plan.wcap);
     KB_CHECK_ARG(used > 0 && used <= V2_SMEM_LIMIT, "conv(v2): plan R=%d TW=%d split=%d dual=%d does not fit", plan.R, plan.TW, plan.n_split, plan.dual);
     if (int rc = build_commands(p)) return rc;
     p.n_raw = 2; p.n_a = 2; p.n_w = 2;
@@ -1004,6 +1007,9 @@ int launch_with_plan(V2Params& p, const V2Plan& plan, const ConvSrcDev* map_src,
     auto grow = [&](int& n, int bytes, int upto) {
         while (n < upto && used + bytes <= V2_SMEM_LIMIT) { ++n; used += bytes; }
     };
+    if (plan.ring == 1 && p.n_stages > 2) grow(p.n_a, p.a_bytes, 3);
+    if (plan.ring == 2) grow(p.n_w, p.w_bytes, 4);
+    if (plan.ring == 3) grow(p.n_raw, p.raw_bytes, 4);
     grow(p.n_raw, p.raw_bytes, 3);
     grow(p.n_w, p.w_bytes, 3);
     grow(p.n_raw, p.raw_bytes, 4);
@@ -1122,7 +1128,7 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
         for (int j = 0; j < p.n_convs; ++j) { k[8 + j] = p.conv[j].Npad; k[12 + j] = p.conv[j].ntaps; }
         k[16] = has_up; k[17] = n_chunks; k[18] = n_tma_chunks; k[19] = n_ops; k[20] = sms; k[21] = autotune != 0; k[22] = n_of_chunks;
     }
-    V2Plan plan = {0, 0, 0, 0};
+    V2Plan plan = {0, 0, 0, 0, 0, 0};
     bool found = false;
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
@@ -1158,12 +1164,32 @@ int v2_launch(V2Params& p, const ConvSrcDev* map_src, int n_maps, const uint8_t*
                 if (rc) continue;
                 if (cand_ms < best_ms) { best_ms = cand_ms; plan = cands[i].plan; }
             }
+            // weight-ring granularity of the winner: three 18 KB slots (3 taps of a 96-filter use) instead of two 24 KB ones were
+            // measured 2 % faster on KB block 2 and slower elsewhere (profiles/r02b_kb_ring_sweep.txt) -- let the clock decide
+            for (int variant = 0; variant < 5; ++variant) {   // 0, 1: slot size; 2-4: which ring takes the spare shared memory first
+                V2Plan alt = plan;
+                if (variant < 2) alt.wcap = variant == 0 ? 18 * 1024 : 12 * 1024;
+                else alt.ring = variant - 1;
+                int rc = launch_with_plan(p, alt, map_src, n_maps, map_cls, has_up, sms, stream, false, of_src, n_of);
+                float alt_ms = 1e30f;
+                for (int rep = 0; rep < 3 && !rc; ++rep) {
+                    KB_CUDA(cudaEventRecord(e0, stream));
+                    rc = launch_with_plan(p, alt, map_src, n_maps, map_cls, has_up, sms, stream, false, of_src, n_of);
+                    KB_CUDA(cudaEventRecord(e1, stream));
+                    if (rc) break;
+                    KB_CUDA(cudaEventSynchronize(e1));
+                    float ms = 0.f;
+                    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                    alt_ms = ms < alt_ms ? ms : alt_ms;
+                }
+                if (!rc && alt_ms < 0.985f * best_ms) { best_ms = alt_ms; plan = alt; }
+            }
             cudaEventDestroy(e0);
             cudaEventDestroy(e1);
         }
         if (const char* ov = getenv("KBNET_V2_PLAN")) {  // debugging aid: "R,TW,n_split,dual"
             int a, b, c, d;
-            if (sscanf(ov, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) plan = {a, b, c, d};
+            if (sscanf(ov, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) plan = {a, b, c, d, 0, 0};
         }
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         if (g_plans.size() < 4096) g_plans.push_back({key, plan});
