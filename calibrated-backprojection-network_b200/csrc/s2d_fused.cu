@@ -30,6 +30,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "conv_common.cuh"
 #include "umma.cuh"
 
@@ -90,7 +92,18 @@ struct FastParams {
     float slope;
     int tiles_x, tiles_y;
     int use_tma;
+    int n_sm;            // SMs of the device (look-ahead distance of the L2 prefetch)
+    long long* stamps;   // KBNET_S2D_STAMPS builds: [cta][6] clock64 at start, data landed, pass 1, pass 2, conv done, + SM id
 };
+#ifdef KBNET_S2D_STAMPS
+#define S2D_STAMP(k)                                                                                                              \
+    do {                                                                                                                          \
+        if (p.stamps != nullptr && threadIdx.x == 0)                                                                              \
+            p.stamps[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 6 + (k)] = clock64();              \
+    } while (0)
+#else
+#define S2D_STAMP(k) do { } while (0)
+#endif
 
 __host__ __device__ inline int w1_bytes(int n_pool, int n_conv) { return (((NF * n_pool + (n_conv - 1) * NF * NF) * 4) + 15) & ~15; }
 
@@ -193,6 +206,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
+}
+
+// L2 prefetch of a tile's TMA box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // ---- weight image: [w1 : 1x1 weights as plain floats, layer 0 as [canonical plane][j], layers >= 1 as [k][j]]
@@ -509,6 +527,14 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     const int C_in = SPEC ? CIN : p.C_in;
     const float slope = p.slope;
 
+    S2D_STAMP(0);
+#ifdef KBNET_S2D_STAMPS
+    if (p.stamps != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.stamps[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 6 + 5] = smid;
+    }
+#endif
     // ---- A. stage the input tile and the weights ---------------------------------------------------------------------
     const bool bulk_w = p.wpack != nullptr;
     const uint32_t wbytes = (uint32_t)(w1_bytes(np, n_conv) + WB_BYTES);
@@ -524,6 +550,24 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             if (C_in > 1) tma_load_3d(smem_u32(s_x1), &tm_x1, x0 - 4, y0 - 1, n * C_in + 1, bar);
         }
         if (bulk_w) bulk_g2s(smem_u32(s_w1), p.wpack, wbytes, bar);
+#ifndef KBNET_S2D_NO_PREFETCH
+        // The CTA that will take over this slot (two CTAs per SM, hardware scheduling in launch order: ~2 x #SMs CTAs ahead)
+        // starts by waiting ~2.2 k clk for its input tile (12 % of a CTA's life, profiles/r02b_s2d_cta_phases.txt): ask for that
+        // tile's boxes now, so that its TMA loads hit in L2.
+        if (p.use_tma) {
+            const unsigned ahead = 2u * (unsigned)p.n_sm;
+            unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + ahead;
+            const unsigned per_n = gridDim.x * gridDim.y;
+            const unsigned nn = lin / per_n;
+            if (nn < gridDim.z) {
+                lin -= nn * per_n;
+                const unsigned ty = lin / gridDim.x, tx = lin - ty * gridDim.x;
+                const int px0 = (int)tx * TW, py0 = (int)ty * TH;
+                tma_prefetch_3d(&tm_z, px0 - 2 - R - 2, py0 - 1 - R, (int)nn * C_in);
+                if (C_in > 1) tma_prefetch_3d(&tm_x1, px0 - 4, py0 - 1, (int)nn * C_in + 1);
+            }
+        }
+#endif
     }
     if (!p.use_tma) {  // shapes the tensor map cannot describe (W % 4 != 0, unaligned base): plain loads, same smem image
         const float* xin = p.x + (size_t)n * C_in * plane;
@@ -542,6 +586,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
     if (!bulk_w) build_weight_image(p.ws, smem + L.w1, tid, NT);
     __syncthreads();
     if (p.use_tma || bulk_w) mbar_wait(bar, 0);
+    S2D_STAMP(1);
 
     // ---- B. pass 1 (vertical): the first warps own one (column, 7-row segment) each; the remaining warps split the raw
     //         channels of the 3x3 conv input to packed bf16 -------------------------------------------------------------
@@ -593,6 +638,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         }
     }
     __syncthreads();
+    S2D_STAMP(2);
 
     // ---- C. pass 2 (horizontal) -> pyramid -> 1x1 chain -> Q chunk planes ----------------------------------------------
     {
@@ -604,6 +650,7 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         }
     }
     __syncthreads();
+    S2D_STAMP(3);
 
     // ---- D. 3x3 conv on mma.sync (bf16 x3 split), LeakyReLU, NCHW stores ---------------------------------------------
     if (tid < CONV_WARPS * 32) {
@@ -697,6 +744,10 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
             }
         }
     }
+#ifdef KBNET_S2D_STAMPS
+    __syncthreads();
+    S2D_STAMP(4);
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -741,10 +792,51 @@ int launch_fast_t(FastParams& p, cudaStream_t stream) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     p.tiles_x = cdiv(p.W, TW);
     p.tiles_y = cdiv(p.H, TH);
+    {
+        int dev = 0, v = 0;
+        p.n_sm = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) p.n_sm = v;
+    }
     KB_CHECK_ARG(p.tiles_y <= 65535 && p.N <= 65535, "s2d: more than 65535 tile rows or samples in one launch");
+#ifdef KBNET_S2D_STAMPS
+    static const char* stamp_file = getenv("KBNET_S2D_STAMPS");   // debugging aid: per-CTA phase times (synchronises!)
+    const size_t n_cta = (size_t)p.tiles_x * p.tiles_y * p.N;
+    if (stamp_file) {
+        KB_CUDA(cudaMalloc(&p.stamps, n_cta * 6 * sizeof(long long)));
+        KB_CUDA(cudaMemsetAsync(p.stamps, 0, n_cta * 6 * sizeof(long long), stream));
+    }
+#endif
     kern<<<dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)p.N), NT, L.total, stream>>>(p, tm_z, tm_x1);
     KB_CUDA(cudaGetLastError());
     count_launch();
+#ifdef KBNET_S2D_STAMPS
+    if (stamp_file && p.stamps) {
+        std::vector<long long> h(n_cta * 6);
+        KB_CUDA(cudaStreamSynchronize(stream));
+        KB_CUDA(cudaMemcpy(h.data(), p.stamps, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.stamps);
+        double sum[4] = {0, 0, 0, 0};
+        for (size_t c = 0; c < n_cta; ++c)
+            for (int k = 0; k < 4; ++k) sum[k] += (double)(h[c * 6 + k + 1] - h[c * 6 + k]);
+        // per SM: first start to last end, and the sum of its CTAs' lifetimes (2 CTAs resident -> ratio ~2 when slots never idle)
+        long long t_min[256], t_max[256]; double life[256]; int cnt[256];
+        for (int i = 0; i < 256; ++i) { t_min[i] = (1ll << 62); t_max[i] = 0; life[i] = 0; cnt[i] = 0; }
+        for (size_t c = 0; c < n_cta; ++c) {
+            const int sm = (int)(h[c * 6 + 5] & 255);
+            t_min[sm] = h[c * 6] < t_min[sm] ? h[c * 6] : t_min[sm];
+            t_max[sm] = h[c * 6 + 4] > t_max[sm] ? h[c * 6 + 4] : t_max[sm];
+            life[sm] += (double)(h[c * 6 + 4] - h[c * 6]); ++cnt[sm];
+        }
+        double span = 0, lifes = 0; int n_sm = 0, cmax = 0;
+        for (int i = 0; i < 256; ++i) if (cnt[i]) { span += (double)(t_max[i] - t_min[i]); lifes += life[i]; ++n_sm; cmax = cnt[i] > cmax ? cnt[i] : cmax; }
+        if (FILE* f = fopen(stamp_file, "a")) {
+            fprintf(f, "s2d R=%d ctas %zu on %d SMs (max %d per SM): mean clocks per CTA: data wait %.0f, pass 1 %.0f, pass 2 %.0f, conv %.0f, total %.0f | "
+                       "per SM: span %.0f clk, sum of CTA lifetimes / span = %.2f\n", R, n_cta, n_sm, cmax, sum[0] / n_cta, sum[1] / n_cta, sum[2] / n_cta,
+                    sum[3] / n_cta, (sum[0] + sum[1] + sum[2] + sum[3]) / n_cta, span / n_sm, lifes / span);
+            fclose(f);
+        }
+    }
+#endif
     return 0;
 }
 
