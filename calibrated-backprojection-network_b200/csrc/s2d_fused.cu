@@ -692,16 +692,26 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
         // Only three output rows are open at any time (row li takes tap rows li .. li + 2); the issue order walks them
         // round-robin so that consecutive HMMAs never touch the same accumulator (a dependent HMMA waits for its predecessor).
         float acc[3][4];
+        // The A fragments of tap row qr + 1 are requested while the HMMAs of row qr still issue: each fragment register set is
+        // reloaded right after its last use (a0l after term 1, a0h after term 2, a1l after term 4, a1h after term 5), so the
+        // ldmatrix / LDS latency hides behind the remaining HMMAs without a second register set (the kernel sits at the register
+        // limit of two CTAs per SM).  Before: the HMMAs' top stall was the shared-memory scoreboard (profiles/r02b_s2d_phases.txt).
+        uint32_t a0h[4], a0l[4], a1h[4], a1l[4];
+        auto load_a0h = [&](int qr) { ldsm_x4(qh + e_s0 + (uint32_t)(qr * QROW * 16), a0h); };
+        auto load_a0l = [&](int qr) { ldsm_x4(ql + e_s0 + (uint32_t)(qr * QROW * 16), a0l); };
+        auto load_a1h = [&](int qr) {
+            ldsm_x2(qh + e_s1 + (uint32_t)(qr * QROW * 16), a1h[0], a1h[1]);
+            a1h[2] = xrow_h[qr * XCP]; a1h[3] = xrow_h[qr * XCP + 1];
+            if (C_in == 1) { a1h[2] &= xmask; a1h[3] &= xmask; }
+        };
+        auto load_a1l = [&](int qr) {
+            ldsm_x2(ql + e_s1 + (uint32_t)(qr * QROW * 16), a1l[0], a1l[1]);
+            a1l[2] = xrow_l[qr * XCP]; a1l[3] = xrow_l[qr * XCP + 1];
+            if (C_in == 1) { a1l[2] &= xmask; a1l[3] &= xmask; }
+        };
+        load_a0h(0); load_a0l(0); load_a1h(0); load_a1l(0);
 #pragma unroll
         for (int qr = 0; qr < LR + 2; ++qr) {
-            uint32_t a0h[4], a0l[4], a1h[4], a1l[4];
-            ldsm_x4(qh + e_s0 + (uint32_t)(qr * QROW * 16), a0h);
-            ldsm_x4(ql + e_s0 + (uint32_t)(qr * QROW * 16), a0l);
-            ldsm_x2(qh + e_s1 + (uint32_t)(qr * QROW * 16), a1h[0], a1h[1]);
-            ldsm_x2(ql + e_s1 + (uint32_t)(qr * QROW * 16), a1l[0], a1l[1]);
-            a1h[2] = xrow_h[qr * XCP]; a1h[3] = xrow_h[qr * XCP + 1];
-            a1l[2] = xrow_l[qr * XCP]; a1l[3] = xrow_l[qr * XCP + 1];
-            if (C_in == 1) { a1h[2] &= xmask; a1h[3] &= xmask; a1l[2] &= xmask; a1l[3] &= xmask; }
             if (qr < LR) {                                 // output row qr opens with tap row 0
                 float (&m)[4] = acc[qr % 3];
                 m[0] = m[1] = m[2] = m[3] = 0.f;
@@ -725,6 +735,12 @@ s2d_fused_kernel(const __grid_constant__ FastParams p, const __grid_constant__ C
                             else              hmma(acc[li % 3], a1h, bl.x, bl.y);
                         }
                     }
+                }
+                if (qr + 1 < LR + 2) {                     // this fragment set is dead now: fetch it for the next tap row
+                    if (term == 1) load_a0l(qr + 1);
+                    else if (term == 2) load_a0h(qr + 1);
+                    else if (term == 4) load_a1l(qr + 1);
+                    else if (term == 5) load_a1h(qr + 1);
                 }
             }
             if (qr >= 2) {                                 // output row qr - 2 is complete: LeakyReLU, 8-byte stores
