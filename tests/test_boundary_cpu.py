@@ -62,6 +62,38 @@ def test_bad_arguments_return_error_codes_not_crashes():
     lib.kbnet_set_autotune(0)
 
 
+def test_operand_format_host_side_contract():
+    """the host-only parts of the operand-format side channel (include/kbnet_b200.h): sizes, shape support, argument checks"""
+    import ctypes
+    lib = _lib.load()
+    BADARG, ALIGN = 10001, 10003
+    # bytes of ONE half: [N][C/8][4 parity planes][H/2][W/2] x 16 B -- the same bytes per value as fp32 halved (2 of 4 bytes)
+    assert lib.kbnet_operand_format_bytes(8, 48, 352, 1216, 0) == 8 * 48 * 352 * 1216 * 2
+    assert lib.kbnet_operand_format_bytes(8, 48, 352, 1216, 1) == 8 * 48 * 352 * 1216 * 2 // 4     # even pixels only
+    assert lib.kbnet_operand_format_bytes(1, 12, 8, 8, 0) == 0                                     # C % 8 != 0
+    assert lib.kbnet_operand_format_bytes(1, 8, 7, 8, 0) == 0 and lib.kbnet_operand_format_bytes(1, 8, 8, 6 + 1, 0) == 0   # odd H / W
+    # which block shapes run as the fused one-launch program (= may use the side channel): the four KITTI / VOID levels do
+    for (ci, cd, cf, fi, fd, ff), (h, w) in zip([(48, 16, 0, 48, 16, 48), (48, 16, 48, 96, 32, 96), (96, 32, 96, 192, 64, 192),
+                                                 (192, 64, 192, 384, 128, 384)], [(352, 1216), (176, 608), (88, 304), (44, 152)]):
+        assert lib.kbnet_kb_operand_format_supported(ci, cd, cf, h, w, fi, fd, ff) == 1
+        assert lib.kbnet_kb_operand_format_supported(ci, cd, cf, h * 480 // 352 // 2 * 2, w * 640 // 1216 // 4 * 4, fi, fd, ff) == 1
+    assert lib.kbnet_kb_operand_format_supported(48, 8, 0, 352, 1216, 48, 16, 48) == 0     # C_d % 16 != 0: unfused launches
+    assert lib.kbnet_kb_operand_format_supported(48, 16, 0, 351, 1216, 48, 16, 48) == 0    # odd height: no equal parity planes
+    assert lib.kbnet_kb_operand_format_supported(48, 16, 0, 352, 1214, 48, 16, 48) == 0    # W % 4 != 0: no TMA
+    # argument checks happen before any CUDA call
+    assert lib.kbnet_to_operand_format(None, 0, 1, 8, 8, 8, None, None, 0, None) == BADARG
+    assert lib.kbnet_from_operand_format(None, None, 1, 8, 8, 8, None, 0, None) == BADARG
+    assert lib.kbnet_to_operand_format(None, 0, 0, 8, 8, 8, None, None, 0, None) == 0      # empty batch
+    assert lib.kbnet_conv3x3_small_forward_of(None, 0, 1, 3, 8, 8, None, 48, 1, 0.2, None, 0, None, None, None) == BADARG
+    of = _lib.KBNetKbOperandFormat()
+    of.image_hi = 256                                                                       # hi without lo
+    args = [256, 16 * 64, 256, 16 * 64, None, 0, None, 256, 1, 16, 16, 0, 8, 8, 256, 16, 256, 16, 256, 256, 16, None, None, None, 0.2,
+            None, 0, 256, 16 * 16, 256, 16 * 16, None, 0]
+    assert lib.kbnet_kb_forward_of(*args, ctypes.byref(of), None) == BADARG and b'hi and its lo' in lib.kbnet_last_error()
+    of.image_lo = 264                                                                       # 8-byte aligned only
+    assert lib.kbnet_kb_forward_of(*args, ctypes.byref(of), None) == ALIGN
+
+
 def _ref_signature_strings():
     # reference src/networks.py:2100-2107, src/net_utils.py:1297-1308, src/kbnet_model.py:63-82
     return {
