@@ -6,6 +6,7 @@
 // its N (profiles/r01_umma_rate_probe.log), on the CUDA cores it is simply HBM-bound (read C planes once, write F planes).
 // One CTA = 64 x 16 output pixels in 4-pixel strips; the C x 18 x 68 input tile and the weights are staged in shared memory.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_common.cuh"
@@ -26,8 +27,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                  : "memory");
 }
 
-template <int F>
-__global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__ CUtensorMap tm, int use_tma, const float* __restrict__ x, long long x_stride_n, int C, int H, int W,
+// NTHR = 256: one 4-pixel strip per thread (any F <= 4).  NTHR = 128 (F == 1, KBNet's output0): one 2-column x 4-row patch per
+// thread -- 6 tile rows x 3 LDS.64 (lanes 8 bytes apart: conflict-free) feed 72 FMAs per channel, a third of the shared-memory
+// wavefronts per FMA of the strip form, whose LDS.64 at a 16-byte lane pitch were 2-way conflicted and set the pace of the kernel.
+template <int F, int NTHR>
+__global__ void __launch_bounds__(NTHR) conv_small_kernel(const __grid_constant__ CUtensorMap tm, int use_tma, const float* __restrict__ x, long long x_stride_n, int C, int H, int W,
                                                          const float* __restrict__ w, int act, float slope, float head_min, float head_ratio,
                                                          float* __restrict__ out, long long out_stride_n) {
     extern __shared__ __align__(128) float smem[];
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
                                                                  // destination must stay 128-byte aligned)
     const int n = blockIdx.z, y0 = blockIdx.y * ST_H, x0 = blockIdx.x * ST_W;
     const size_t plane = (size_t)H * W;
-    for (int i = threadIdx.x; i < C * F * 12; i += blockDim.x) {
+    for (int i = threadIdx.x; i < C * F * 12; i += NTHR) {
         const int t = i % 12, r = i / 12, f = r % F, c = r / F;
         s_w[i] = t < 9 ? __ldg(w + ((size_t)f * C + c) * 9 + t) : 0.f;
     }
@@ -55,11 +59,11 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
     // fallback tile load (tensors TMA cannot describe): batches of 8 independent loads per thread in flight (a load -> store loop would
     // leave ONE load in flight per warp and the kernel latency-bound); PWd, PHt are compile-time constants -> mul/shift index split
     const int total = use_tma ? 0 : C * PHt * PWd;
-    for (int base = threadIdx.x; base < total; base += 256 * 8) {
+    for (int base = threadIdx.x; base < total; base += NTHR * 8) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * 256;
+            const int idx = base + u * NTHR;
             v[u] = 0.f;
             if (idx < total) {
                 const int r = idx / PWd, tx = idx - r * PWd;
@@ -70,11 +74,59 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * 256;
+            const int idx = base + u * NTHR;
             if (idx < total) s_x[idx] = v[u];
         }
     }
     __syncthreads();
+    if (F == 1 && NTHR == 128) {
+        const int u = threadIdx.x & 31, rg = threadIdx.x >> 5;   // output columns 2u, 2u + 1; output rows 4 rg .. 4 rg + 3
+        float acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float4* wp = reinterpret_cast<const float4*>(s_w + c * 12);
+            const float4 wa = wp[0], wb = wp[1], wd = wp[2];
+            const float wv[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wd.x};
+            // tile column of output column j and tap kx: j + 3 + kx (the tile starts at image column x0 - 4); v[k] = tile column 2u + 2 + k
+            const float* xs = s_x + (c * PHt + 4 * rg) * PWd + 2 * u + 2;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const float2 t0 = *reinterpret_cast<const float2*>(xs + r * PWd), t1 = *reinterpret_cast<const float2*>(xs + r * PWd + 2),
+                             t2 = *reinterpret_cast<const float2*>(xs + r * PWd + 4);
+                const float v[6] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y};
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int i = r - ky;                     // tile row 4 rg + r is tap row ky of output row 4 rg + i
+                    if (i >= 0 && i < 4) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            acc[i][e] = fmaf(v[e + 1], wv[ky * 3 + 0], fmaf(v[e + 2], wv[ky * 3 + 1], fmaf(v[e + 3], wv[ky * 3 + 2], acc[i][e])));
+                    }
+                }
+            }
+        }
+        const int gx = x0 + 2 * u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gy = y0 + 4 * rg + i;
+            if (gy >= H || gx >= W) continue;
+            float o[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                o[e] = acc[i][e];
+                if (act == 1) o[e] = leaky(o[e], slope);
+                if (act == 2) o[e] = head_min / (1.f / (1.f + expf(-o[e])) + head_ratio);
+            }
+            float* dst = out + (size_t)n * out_stride_n + (size_t)gy * W + gx;
+            if (gx + 1 < W && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+            else {
+                dst[0] = o[0];
+                if (gx + 1 < W) dst[1] = o[1];
+            }
+        }
+        return;
+    }
     // 256 threads: strips of 4 pixels (16 strips per row, 16 rows)
     const int px = (threadIdx.x & 15) * 4, py = threadIdx.x >> 4;
     float acc[4][F];
@@ -161,15 +213,17 @@ int conv_small_launch(const float* x, long long x_stride_n, int N, int C, int H,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
     }
-#define KB_SMALL(FF)                                                                                                                          \
+#define KB_SMALL(FF, NTHR)                                                                                                                    \
     do {                                                                                                                                      \
-        KB_CUDA(cudaFuncSetAttribute(conv_small_kernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-        conv_small_kernel<FF><<<grid, 256, smem, stream>>>(tm, use_tma, x, x_stride_n, C, H, W, w, act, slope, head_min, head_ratio, out, out_stride_n);   \
+        KB_CUDA(cudaFuncSetAttribute(conv_small_kernel<FF, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        conv_small_kernel<FF, NTHR><<<grid, NTHR, smem, stream>>>(tm, use_tma, x, x_stride_n, C, H, W, w, act, slope, head_min, head_ratio, out, out_stride_n);   \
     } while (0)
-    if (F == 1) KB_SMALL(1);
-    else if (F == 2) KB_SMALL(2);
-    else if (F == 3) KB_SMALL(3);
-    else KB_SMALL(4);
+    static const bool strips_f1 = getenv("KBNET_SMALL_STRIPS") != nullptr;   // A/B aid: the 4-pixel-strip form for F == 1 as well
+    if (F == 1 && !strips_f1) KB_SMALL(1, 128);
+    else if (F == 1) KB_SMALL(1, 256);
+    else if (F == 2) KB_SMALL(2, 256);
+    else if (F == 3) KB_SMALL(3, 256);
+    else KB_SMALL(4, 256);
 #undef KB_SMALL
     KB_CUDA(cudaGetLastError());
     count_launch();
