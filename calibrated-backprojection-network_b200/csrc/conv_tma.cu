@@ -103,6 +103,7 @@ struct V2Conv {
     uint8_t* of_hi;
     uint8_t* of_lo;
     int of_cg, of_even;
+    int T, pad_t;      // taps of this convolution per weight-ring slot (a slot holds p.w_bytes: convolutions with fewer filters pack more taps)
 };
 // One entry of the MMA issuer's command table (built on the host for the chosen tile plan, read from the kernel parameters):
 // one tap of one convolution for all M-blocks of the tile.  The issuing thread does no bookkeeping beyond what the flags ask for.
@@ -135,6 +136,29 @@ struct V2Params {
     int of_box_bytes;     // bytes of one operand-format box = P * (R + 1) * 16
     long long* dbg;       // optional timeline buffer (KBNET_V2_TIMELINE): [role 0..4][4096] clock64 stamps of CTA 0
 };
+// Weight-ring slot formation, shared by the weight producer (device) and build_commands (host): the taps of a use go into slots
+// of cv.T taps; the LAST slot of a use also takes the following uses of the same stage as long as each of them is a single
+// slot by itself and the bytes fit -- one mbarrier hand-over instead of several (a hop costs the MMA issuer ~250 clk).
+// Returns the number of following uses merged into the slot that starts at tap t0 of use u, and the slot's total bytes.
+__host__ __device__ inline int w_slot_merge(const V2Params& p, const V2Stage& st, int u, int t0, int nt, int ntap, uint32_t* total_bytes) {
+    uint32_t total = (uint32_t)nt * (uint32_t)p.conv[st.use[u].conv].Nsl * 64u;
+    int n_merge = 0;
+    if (t0 + nt >= ntap) {
+        for (int v = u + 1; v < st.n_use; ++v) {
+            const V2Conv& c2 = p.conv[st.use[v].conv];
+            unsigned m = st.use[v].tapmask;
+            int nt2 = 0;
+            for (; m; m &= m - 1) ++nt2;
+            const uint32_t b2 = (uint32_t)nt2 * (uint32_t)c2.Nsl * 64u;
+            if (nt2 > c2.T || total + b2 > (uint32_t)p.w_bytes) break;
+            total += b2;
+            ++n_merge;
+        }
+    }
+    *total_bytes = total;
+    return n_merge;
+}
+
 struct alignas(64) V2Maps {
     CUtensorMap m[V2_MAX_MAPS];
 };
@@ -499,26 +523,37 @@ __global__ void __launch_bounds__(cta_threads(GEO), 1) conv_v2_kernel(const __gr
                 const int split = (int)(tile % p.n_split);
                 for (int s = 0; s < p.n_stages; ++s) {
                     const V2Stage& st = p.stage[s];
-                    for (int u = 0; u < st.n_use; ++u) {
+                    for (int u = 0; u < st.n_use;) {
                         const V2Use us = st.use[u];
                         const V2Conv& cv = p.conv[us.conv];
                         const int ntap = __popc((unsigned)us.tapmask);
-                        const int Tu = ntap < p.T ? ntap : p.T;
-                        const uint32_t piece = (uint32_t)cv.Nsl * 64u;              // one tap of this filter-split part
-                        const size_t tile_b = (size_t)cv.Npad * 64;
+                        const int Tu = ntap < cv.T ? ntap : cv.T;
+                        int n_merge = 0;
                         for (int t0 = 0; t0 < ntap; t0 += Tu, w_r.advance((uint32_t)p.n_w)) {
                             const int nt = ntap - t0 < Tu ? ntap - t0 : Tu;
                             const int ws = (int)w_r.slot;
+                            uint32_t total;
+                            n_merge = w_slot_merge(p, st, u, t0, nt, ntap, &total);
                             V2_WAIT_RELAXED(BAR(B_W_EMPTY + ws), w_r.phase ^ 1u, 32);
-                            const uint8_t* src = cv.wpack + (size_t)(us.wtile + t0) * tile_b + (size_t)split * piece;
-                            const uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
-                            mbar_arrive_expect_tx(BAR(B_W_FULL + ws), (uint32_t)nt * piece);
-                            if (p.n_split == 1) {
-                                bulk_g2s(dst, src, (uint32_t)nt * piece, BAR(B_W_FULL + ws));  // consecutive taps are consecutive tiles
-                            } else {
-                                for (int k = 0; k < nt; ++k) bulk_g2s(dst + (uint32_t)k * piece, src + (size_t)k * tile_b, piece, BAR(B_W_FULL + ws));
+                            uint32_t dst = smem_u32(sW + (size_t)ws * p.w_bytes);
+                            mbar_arrive_expect_tx(BAR(B_W_FULL + ws), total);
+                            // this use's taps [t0, t0 + nt), then every tap of the merged following uses
+                            for (int v = u; v <= u + n_merge; ++v) {
+                                const V2Use uv = st.use[v];
+                                const V2Conv& cw = p.conv[uv.conv];
+                                const uint32_t piece = (uint32_t)cw.Nsl * 64u;              // one tap of this filter-split part
+                                const size_t tile_b = (size_t)cw.Npad * 64;
+                                const int tv0 = v == u ? t0 : 0, ntv = v == u ? nt : __popc((unsigned)uv.tapmask);
+                                const uint8_t* src = cw.wpack + (size_t)(uv.wtile + tv0) * tile_b + (size_t)split * piece;
+                                if (p.n_split == 1) {
+                                    bulk_g2s(dst, src, (uint32_t)ntv * piece, BAR(B_W_FULL + ws));  // consecutive taps are consecutive tiles
+                                } else {
+                                    for (int k = 0; k < ntv; ++k) bulk_g2s(dst + (uint32_t)k * piece, src + (size_t)k * tile_b, piece, BAR(B_W_FULL + ws));
+                                }
+                                dst += (uint32_t)ntv * piece;
                             }
                         }
+                        u += 1 + n_merge;
                     }
                 }
             }
@@ -857,6 +892,22 @@ long long apply_geometry(V2Params& p, int R, int TW, int n_split, int dual, bool
     for (int j = 0; j < p.n_convs; ++j) max_taps = p.conv[j].ntaps > max_taps ? p.conv[j].ntaps : max_taps;
     if (p.T > max_taps) p.T = max_taps;
     p.w_bytes = roundup(max_nsl * 64 * p.T, 128);
+    if (p.n_convs > 1) {   // several small uses per stage (the four parity convolutions of a 64 -> 12 up-convolution): room for a whole stage
+        int stage_max = 0;
+        for (int s = 0; s < p.n_stages; ++s) {
+            int sum = 0;
+            for (int u = 0; u < p.stage[s].n_use; ++u)
+                sum += __builtin_popcount((unsigned)p.stage[s].use[u].tapmask) * p.conv[p.stage[s].use[u].conv].Nsl * 64;
+            stage_max = sum > stage_max ? sum : stage_max;
+        }
+        if (stage_max <= wcap && roundup(stage_max, 128) > p.w_bytes) p.w_bytes = roundup(stage_max, 128);
+    }
+    for (int j = 0; j < p.n_convs; ++j) {   // per-convolution taps per slot: fewer slot hand-overs for the convolutions with few filters
+        V2Conv& cv = p.conv[j];
+        const int fit = p.w_bytes / (cv.Nsl * 64);
+        cv.T = fit >= 9 ? 9 : (fit >= 4 ? 4 : (fit >= 3 ? 3 : (fit >= 2 ? 2 : 1)));
+        if (cv.T < p.T) cv.T = p.T;
+    }
     p.tiles_x = cdiv(p.Wout, TW);
     p.tiles_y = cdiv(p.Hout, R);
     p.n_tiles = (long long)p.N * p.tiles_x * p.tiles_y * n_split;
@@ -957,26 +1008,43 @@ int build_commands(V2Params& p) {
     for (int s = 0; s < p.n_stages; ++s) {
         const V2Stage& st = p.stage[s];
         const int first_cmd = n;
+        int merged_left = 0;          // uses still to come that share the currently open weight slot
+        uint32_t slot_off16 = 0;      // where the next merged use starts inside that slot (16-byte units)
         for (int u = 0; u < st.n_use; ++u) {
             const V2Use& us = st.use[u];
             const V2Conv& cv = p.conv[us.conv];
             const uint32_t piece16 = (uint32_t)cv.Nsl * 4u;   // one tap of weights, in 16-byte units
             const uint32_t idesc = idesc_bf16_f32(128, p.dual ? 2 * cv.Nsl : cv.Nsl);
-            int left = __builtin_popcount((unsigned)us.tapmask);
-            const int Tu = left < p.T ? left : p.T;
-            int cnt = 0;
+            const int ntap = __builtin_popcount((unsigned)us.tapmask);
+            int left = ntap;
+            const int Tu = left < cv.T ? left : cv.T;
+            const bool follower = merged_left > 0;   // this use's (single) slot is the tail of the previous use's last slot
+            if (follower) --merged_left;
+            int cnt = 0, t0 = 0;
             uint32_t accum = us.first ? 0u : CMD_ACCUM;
             for (uint32_t t = 0; t < 9; ++t) {
                 if (!((us.tapmask >> t) & 1u)) continue;
                 KB_CHECK_ARG(n < V2_MAX_CMDS, "conv(v2): program too long for the command table");
-                uint32_t flags = accum | (cnt == 0 ? CMD_WAIT_W : 0u);
-                const uint32_t a_rel = tap_offset(t / 3, t % 3), b_rel = (uint32_t)cnt * piece16;
+                uint32_t flags = accum | ((cnt == 0 && !follower) ? CMD_WAIT_W : 0u);
+                if (cnt == 0 && !follower) {   // a slot opens: does it take following uses?
+                    const int nt = ntap - t0 < Tu ? ntap - t0 : Tu;
+                    uint32_t total;
+                    merged_left = w_slot_merge(p, st, u, t0, nt, ntap, &total);
+                    slot_off16 = (uint32_t)nt * piece16;
+                }
+                const uint32_t a_rel = tap_offset(t / 3, t % 3), b_rel = (follower ? slot_off16 : 0u) + (uint32_t)cnt * piece16;
                 KB_CHECK_ARG(a_rel < 0x10000u && b_rel < 0x10000u && cv.col < 0x10000, "conv(v2): command field overflow");
                 accum = CMD_ACCUM;
                 --left;
-                if (++cnt == Tu || left == 0) { flags |= CMD_COMMIT_W; cnt = 0; }
+                if (++cnt == Tu || left == 0) {
+                    // the slot closes with its last occupant: this use, unless followers share it
+                    if (!(left == 0 && merged_left > 0)) flags |= CMD_COMMIT_W;
+                    t0 += cnt;
+                    cnt = 0;
+                }
                 p.cmd[n++] = make_uint4(a_rel | (flags << 16), b_rel | ((uint32_t)cv.col << 16), idesc, 0u);
             }
+            if (follower) slot_off16 += (uint32_t)ntap * piece16;
         }
         KB_CHECK_ARG(n > first_cmd, "conv(v2): stage %d has no taps", s);
         p.cmd[first_cmd].x |= (uint32_t)CMD_WAIT_A << 16;
