@@ -1,22 +1,24 @@
 // Fused SparseToDensePool forward for sm_100a -- ONE kernel for reference src/networks.py:2168-2196.
 //
-// Per CTA: a 12 x 64 output tile of one sample, 256 threads, ~80 KB of shared memory (2 CTAs per SM).
+// Per CTA: a 16 x 64 output tile of one sample, 320 threads, ~95 KB of shared memory, 92 registers (2 CTAs per SM).
 //
 //   A. TMA      the sparse-depth halo tile and the second raw channel are staged into shared memory by
 //               cp.async.bulk.tensor (3-D tiled tensor map over [N*C, H, W], out-of-image elements zero-filled), the
-//               pre-packed weights by one cp.async.bulk, all completing on one mbarrier.
-//   B. pass 1   vertical nested-window sweep: one thread per tile column and 5-row segment produces, for every pool
-//               radius, the column min / max (FMNMX3.NAN: one instruction per radius step) -> V planes in smem.
-//               The raw x channels are split to bf16 hi/lo for the 3x3 conv in the same phase.
-//   C. pass 2   horizontal sweep on 4-pixel strips, all in registers: pool pyramid -> 999->0 fix -> the 1x1 fusion chain
-//               (exact fp32, packed FFMA2 on pixel pairs, weights broadcast from smem) -> LeakyReLU -> Q (8 channels),
-//               written to smem as bf16 hi/lo "chunk planes" (16 bytes = 8 channels of one pixel).
+//               pre-packed weights by one cp.async.bulk, all completing on one mbarrier; the tile of the CTA that will take
+//               over this slot is prefetched into L2 (cp.async.bulk.prefetch.tensor).
+//   B. pass 1   vertical nested-window sweep: one thread per tile column and 6-row (R <= 8) / 9-row segment produces, for
+//               every pool radius, the column min / max (FMNMX3.NAN: one instruction per radius step) -> V planes in smem.
+//               The remaining warps split the raw x channels to bf16 hi/lo for the 3x3 conv in the same phase.
+//   C. pass 2   horizontal sweep on 4-pixel strips, all in registers: the four windows of a strip share their core
+//               (RK + 5 instead of 4 RK min / max per plane) -> 999->0 fix -> the 1x1 fusion chain (exact fp32, packed FFMA2 on
+//               pixel pairs, weights broadcast from smem) -> LeakyReLU -> Q (8 channels), written to smem as bf16 hi/lo
+//               "chunk planes" (16 bytes = 8 channels of one pixel; even columns then odd columns of a row).
 //   D. 3x3 conv on the legacy tensor path (mma.sync m16n8k16 bf16, fp32 accumulate) with the 3-term operand split
 //               a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (16 mantissa bits per operand, ~1e-5 relative).  N = 8 filters is
 //               exactly one n8 tile; K = 9 taps x 8 Q channels + 3 rows x (3 dx x C_in) raw channels = 96 = 6 k16 steps.
-//               A fragments come from the chunk planes with ldmatrix (a tap is a row-address shift, no im2col) and are
-//               reused for the three output rows a Q row contributes to; the B fragments live in registers.
-//               Epilogue: LeakyReLU -> NCHW stores (each store instruction writes four full 32-byte sectors).
+//               A fragments come from the chunk planes with ldmatrix (a tap is a row-address shift, no im2col), are reused
+//               for the three output rows a Q row contributes to and are re-loaded in place right after their last use; the
+//               B fragments live in registers.  Epilogue: LeakyReLU -> 8-byte NCHW stores.
 //
 // Why not tcgen05 here: with N = 8 a tcgen05.mma is bounded by streaming its 128 x 16 A tile from shared memory
 // (>= 47 clk per 128 pixels per k16 step measured, profiles/r01_umma_probe.md) -- 3x slower than mma.sync for this shape
